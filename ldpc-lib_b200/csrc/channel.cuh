@@ -1,0 +1,150 @@
+// On-device channel: counter-based N(0,1) generator, BPSK / QAM-4 LLR and the exact Gray-PAM x PAM
+// QAM-16/64/256 bit-LLR.  Device functions shared by the stand-alone kernels in channel.cu and by the
+// decoders' first load (the LLRs of a simulated frame never exist in HBM).
+//
+// Reference behaviour restated here:
+//   BPSK / QAM-4 LLR          bp_simulation.cpp:600-612     llr = -2 (sigma n + 2 c - 1) / sigma^2, c = 0
+//   received QAM symbol       bp_simulation.cpp:621-625     intended channel r = s + sigmaQAM n (the
+//                                                           reference accumulates unscaled noise: SURVEY fact 6)
+//   Demodulate                QAM_demodulator.cpp:99-566    with m = log2(Q); caller negates (:627-628)
+//   puncturing                bp_simulation.cpp:697-710
+// The reference draws its noise from a global std::mt19937 (commons_portable.cpp:174-178); that stream
+// cannot be reproduced in parallel, so noise sample i of frame f is instead
+//   Philox4x32-10(key = seed, counter = (i / 4, f_lo, f_hi, stream))[i % 4]  ->  Box-Muller (fp32),
+// which makes results independent of batch size, launch geometry and GPU count.
+#pragma once
+#include <cstdint>
+#include "kernels.h"
+
+namespace ldpcb200 {
+
+struct u32x4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; r++) {
+        unsigned long long p0 = (unsigned long long)M0 * c0, p1 = (unsigned long long)M1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    u32x4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+#ifdef __CUDACC__
+// two N(0,1) samples from two 32-bit words
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1)
+{
+    float u = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) / 2^32
+    float r = sqrtf(__fmul_rn(-2.0f, logf(u)));
+    float s, c;
+    sincospif(__fmul_rn(__uint2float_rn(b), 4.656612873077393e-10f), &s, &c);                     // angle = 2 pi b / 2^32
+    z0 = __fmul_rn(r, c);
+    z1 = __fmul_rn(r, s);
+}
+
+// noise sample `idx` of frame `frame`
+__device__ __forceinline__ float channel_noise(const ChannelParams& ch, unsigned long long frame, uint32_t idx)
+{
+    u32x4 w = philox4x32_10(idx >> 2, (uint32_t)frame, (uint32_t)(frame >> 32), ch.stream,
+                            (uint32_t)ch.seed, (uint32_t)(ch.seed >> 32));
+    float z0, z1;
+    if (idx & 2) box_muller(w.z, w.w, z0, z1); else box_muller(w.x, w.y, z0, z1);
+    return (idx & 1) ? z1 : z0;
+}
+
+// four consecutive noise samples idx4*4 .. idx4*4+3
+__device__ __forceinline__ void channel_noise4(const ChannelParams& ch, unsigned long long frame, uint32_t idx4, float z[4])
+{
+    u32x4 w = philox4x32_10(idx4, (uint32_t)frame, (uint32_t)(frame >> 32), ch.stream,
+                            (uint32_t)ch.seed, (uint32_t)(ch.seed >> 32));
+    box_muller(w.x, w.y, z[0], z[1]);
+    box_muller(w.z, w.w, z[2], z[3]);
+}
+
+__device__ __forceinline__ float bpsk_llr(const ChannelParams& ch, float n)
+{
+    return __fmul_rn(__fmaf_rn(-ch.sigma, n, 1.0f), ch.llr_scale);
+}
+
+// one output of Demodulate's if-ladder (e.g. QAM_demodulator.cpp:215-239)
+__device__ __forceinline__ double demod_out(double p0, double p1, double T, int out_type)
+{
+    if (p0 == 0.0) return out_type == 0 ? T : 1.0;
+    if (p1 == 0.0) return out_type == 0 ? -T : 0.0;
+    return out_type == 0 ? log(p1 / p0) : p1;
+}
+
+// Exact bit metrics of one PAM component (I or Q) of a Gray-mapped QAM symbol, m = 4, 6 or 8 bits per
+// symbol: o[0 .. m/2) in the order Demodulate writes them.  Evaluation order follows
+// QAM_demodulator.cpp:181-199 (t = x - L; t *= t; t /= N0; P normalised before the bit sums) and the
+// summation trees of :203-561, so only exp/log can differ from the reference, in the last ulp.
+__device__ __forceinline__ void pam_demod(double x, double N0, double T, int m, int out_type, double* o)
+{
+    const int SQ = 1 << (m >> 1);
+    double P[16];
+    double sum = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (i < SQ) {
+            double t = x - (double)(2 * i - (SQ - 1));
+            t *= t;
+            t /= N0;
+            P[i] = t < T ? exp(-t) : 0.0;
+            sum += P[i];
+        } else P[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (i < SQ) P[i] /= sum;
+    if (m == 4) {
+        o[0] = demod_out(P[0] + P[1], P[2] + P[3], T, out_type);
+        o[1] = demod_out(P[0] + P[3], P[1] + P[2], T, out_type);
+    } else if (m == 6) {
+        double p12 = P[0] + P[1], p34 = P[2] + P[3], p56 = P[4] + P[5], p78 = P[6] + P[7];
+        o[0] = demod_out(p12 + p34, p56 + p78, T, out_type);
+        o[1] = demod_out(p12 + p78, p34 + p56, T, out_type);
+        o[2] = demod_out(P[0] + P[3] + P[4] + P[7], P[1] + P[2] + P[5] + P[6], T, out_type);
+    } else {
+        double p12 = P[0] + P[1], p34 = P[2] + P[3], p56 = P[4] + P[5], p78 = P[6] + P[7];
+        double p9A = P[8] + P[9], pBC = P[10] + P[11], pDE = P[12] + P[13], pFG = P[14] + P[15];
+        double p1234 = p12 + p34, p5678 = p56 + p78, p9ABC = p9A + pBC, pDEFG = pDE + pFG;
+        o[0] = demod_out(p1234 + p5678, p9ABC + pDEFG, T, out_type);
+        o[1] = demod_out(p1234 + pDEFG, p5678 + p9ABC, T, out_type);
+        o[2] = demod_out(p12 + p78 + p9A + pFG, p34 + p56 + pBC + pDE, T, out_type);
+        o[3] = demod_out(P[0] + P[3] + P[4] + P[7] + P[8] + P[11] + P[12] + P[15],
+                         P[1] + P[2] + P[5] + P[6] + P[9] + P[10] + P[13] + P[14], T, out_type);
+    }
+}
+
+// QAM-16/64/256 LLR of bit i (kept out of line: it is heavy in registers and only used by C3-like runs)
+static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, unsigned long long frame, int i)
+{
+    // QAM-16/64/256: bit i lives in symbol i / m; the first m/2 bits ride on I, the rest on Q
+    const int half = ch.m >> 1;
+    int sym = i / ch.m, r = i - sym * ch.m;
+    int comp = r >= half;
+    int bit = r - comp * half;
+    float nz = channel_noise(ch, frame, (uint32_t)(2 * sym + comp));
+    // all-zero bits -> natural index 0 -> gray[0] = 0 -> coordinate -(sqrt(Q) - 1)  (QAM_modulator.cpp:127-140)
+    double x = (double)nz * ch.sigma_d - (double)((1 << half) - 1);
+    double o[4];
+    pam_demod(x, 2.0 * ch.sigma_d * ch.sigma_d, ch.T, ch.m, 0, o);
+    return (float)(-o[bit]);
+}
+
+// Channel LLR (log P0/P1, the decoder-side sign) of bit i of frame f for the all-zero codeword.
+__device__ __forceinline__ float channel_llr(const ChannelParams& ch, unsigned long long frame, int i)
+{
+    if (i >= ch.punct_start) return ch.punct_value;
+    if (ch.m <= 2) return bpsk_llr(ch, channel_noise(ch, frame, (uint32_t)i));
+    return channel_llr_qam(ch, frame, i);
+}
+#endif
+
+} // namespace ldpcb200
