@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Throughput of the Monte-Carlo BP hot path on B200 -- decoded information Gbit/s, max 10 iterations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): REF-32x16-B base matrix (configs/ref32x16_b.jsonx) lifted to
+Z = 256 (N = 8192, K = 4096), LMS_DEC semantics (layered offset min-sum, lmin_sum_decod_qc_lm), BPSK/AWGN
+at Eb/N0 = 2.0 dB, all-zero codeword, 2^20 frames per GPU per step, every frame run for exactly 10
+iterations (LDPCB200_NO_EARLY_EXIT: the worst case the 100 Gbit/s target is quoted on).
+
+One JSON line on stdout (rank 0):
+  value     device-resident decode: fp32 LLRs already in HBM (32 GiB per GPU, > L2, so every step streams
+            them from HBM), ldpcb200_decode_batch with device pointers -> packed decisions + iteration counts
+  e2e       the reference-facing call of this path, ldpcb200_simulate (= one round of bp_simulation's frame
+            loop): host parameter block in, noise + LLR generated inside the decoder's first load, host
+            counters and per-frame records out (D2H inside the timed region), + the NCCL all-reduce of the
+            counters when N > 1
+  roofline  HBM byte roofline of the decode kernel (it is instruction-issue bound; the issue
+            roofline is in "issue")
+  cpu_baseline   the compiled reference (oracle/_ref) decoding a bounded sample of the same LLR buffers on
+            the host cores, and a parity check of the GPU results on that sample
+`--impl reference` times the unmodified reference bp_simulation() on all host cores instead.
+"""
+import argparse
+import importlib.util
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CODE, Z, SNR_DB, MAXITER, DECODER = "ref32x16_b", 256, 2.0, 10, 8      # 8 = LMS_DEC
+FRAMES_PER_GPU = 1 << 20
+METRIC, UNIT = "decoded_info_gbps_10iter", "Gbit/s"
+
+
+def load_binding():
+    spec = importlib.util.spec_from_file_location("pyldpcb200", os.path.join(ROOT, "ldpc-lib_b200", "pyldpcb200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["pyldpcb200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_config(n_gpus, frames):
+    return {"workload": "C2: REF-32x16-B 16x32 Z=256 (N=8192,K=4096), LMS_DEC layered offset min-sum, max 10 iters, "
+                        "BPSK/AWGN Eb/N0=2.0 dB, all-zero codeword",
+            "frames_per_gpu_per_step": frames, "fixed_iterations": True,
+            "l2": "inputs (32 KiB/frame fp32 LLR, 32 GiB/GPU) larger than L2", "parallelism": "frames sharded x%d" % n_gpus}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    """One host core: the unmodified reference bp_simulation() (oracle/_ref) on `frames` frames."""
+    seed, frames = args
+    from oracle import pyoracle as po
+    from codes import load_code
+    hd, _ = load_code(CODE)
+    t0 = time.perf_counter()
+    # n_frame_errors huge, reference_frame_error 1.0: neither stop rule fires; the loop runs frames + 1 frames
+    po.ref_bp_simulation(hd, Z, MAXITER, 1 << 30, frames - 1, SNR_DB, 1.0, DECODER, seed=seed)
+    return time.perf_counter() - t0
+
+
+def _decode_worker(args):
+    """One host core: the reference's lmin_sum_decod_qc_lm on a slice of given LLR buffers."""
+    llr, = args
+    from oracle import pyoracle as po
+    from codes import load_code
+    hd, _ = load_code(CODE)
+    t0 = time.perf_counter()
+    r = po.ref_decode(DECODER, hd, Z, llr, MAXITER, fresh=False, want_post=False)
+    return time.perf_counter() - t0, r["hard"], r["iters"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    if not po.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libldpcref.so missing (build with make -C oracle ref)"}))
+        return
+    cores = os.cpu_count() or 1
+    frames_per_core = 200                       # ~1.5 s of CPU work per core per step at ~0.13 k frames/s/core
+    K = (32 - 16) * Z
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, [(1000 * step + i + 1, frames_per_core) for i in range(cores)])
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    frames = frames_per_core * cores * args.steps
+    val = frames * K / total / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args.gpus, frames_per_core * cores),
+                           fixed_iterations=False, note="reference bp_simulation() cannot disable its syndrome early exit"),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": "%d frames per core per step through the unmodified bp_simulation() (mt19937 noise, "
+                                       "lmin_sum_decod_qc_lm, error counting), one process per core" % frames_per_core},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, smax, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    L = load_binding()
+    from codes import load_code
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    hd, _ = load_code(CODE)
+    b, c = hd.shape
+    frames = args.frames
+    dec = L.Decoder(hd, Z, DECODER, precision=32, device=local)
+    info = dec.kernel_info()
+    N, K = dec.N, dec.K
+    bytes_per_frame = 4 * N + N // 8 + 4                              # LLR in, hard bits out, iteration count
+
+    # resident inputs: this rank's frames of the stream (seed 1, stream 0), generated once on the device
+    llr = torch.empty((frames, N), dtype=torch.float32, device=dev)
+    first = rank * frames
+    chunk = 1 << 16
+    for f0 in range(0, frames, chunk):
+        n = min(chunk, frames - f0)
+        dec.generate_llr(SNR_DB, n, seed=1, stream=0, first_frame=first + f0, out=llr[f0:f0 + n])
+    hard = torch.empty((frames, dec.nwords), dtype=torch.int32, device=dev)
+    iters = torch.empty(frames, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(6, dtype=torch.int64, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_value():
+        dec.decode_device(llr, MAXITER, hard_words=hard, iters=iters, no_early_exit=True)
+        return dec.last_kernel_ms()
+
+    def step_e2e(i):
+        r = dec.simulate(SNR_DB, frames, MAXITER, seed=1, stream=1, first_frame=(i * world + rank) * frames,
+                         no_early_exit=True, want_per_frame=True)
+        if world > 1:                                                # the path's only exchange: error counters
+            t = torch.tensor([r["frames"], r["frame_errors"], r["info_bit_errors"], r["undetected"], r["iter_sum"], r["bit_errors"]],
+                             dtype=torch.int64, device=dev)
+            dist.all_reduce(t)
+            t = t.cpu()
+        return r
+
+    for _ in range(args.warmup):
+        step_value()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        ms, nl = step_value()
+        dev_ms += ms
+        launches += nl
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    wall_ms = 1e3 * (t1 - t0)
+
+    # the same decode with the reference's syndrome early exit (informational)
+    dec.decode_device(llr, MAXITER, hard_words=hard, iters=iters)
+    ee_ms, _ = dec.last_kernel_ms()
+    avg_iters = float(iters.abs().float().mean().item())
+    fer_proxy = float((iters < 0).float().mean().item())
+
+    # e2e through simulate()
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(1000 + i)
+    barrier()
+    t2 = time.perf_counter()
+    e2e_launches = 0
+    for i in range(args.steps):
+        step_e2e(i)
+        e2e_launches += dec.last_kernel_ms()[1]
+    barrier()
+    t3 = time.perf_counter()
+    e2e_ms = 1e3 * (t3 - t2)
+
+    def maxred(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dev_ms, wall_ms, e2e_ms, ee_ms = maxred(dev_ms), maxred(wall_ms), maxred(e2e_ms), maxred(ee_ms)
+
+    if rank == 0:
+        total_frames = frames * world * args.steps
+        value = total_frames * K / (wall_ms * 1e-3) / 1e9
+        kernel_ms = dev_ms / args.steps
+        achieved = frames * bytes_per_frame / (kernel_ms * 1e-3) / 1e9
+        peak, peak_src = 6650.0, "fallback"
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "measured"
+        except Exception:
+            pass
+        sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+        edge_updates = frames * dec.E * Z * MAXITER / (kernel_ms * 1e-3)
+        issue_peak = 148 * 4 * 32 * sm_hz * 1e6                      # thread-instructions / s
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(world, frames),
+                "kernel": dict(info, kernel_ms_per_step=kernel_ms, name="lms_fast_kernel" if info["fast"] else "generic_minsum_kernel"),
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": total_frames * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 72,
+                        "d2h_bytes_per_step": 48 + 4 * frames, "gpu_launches": e2e_launches,
+                        "call": "ldpcb200_simulate (host sim-params -> host counters + per-frame records)"},
+                "early_exit": {"value": frames * world * K / (ee_ms * 1e-3) / 1e9, "unit": UNIT, "avg_iterations": avg_iters,
+                               "frame_failure_rate": fer_proxy},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame},
+                "issue": {"edge_updates_per_s": edge_updates, "thread_instr_peak_per_s": issue_peak,
+                          "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(dec, llr, hard, iters, K)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(dec, llr, hard, iters, K):
+    """The compiled reference on the host cores, on the first frames of the same LLR buffers; also checks the
+    GPU's early-exit results on that sample against it."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    per_core = 160
+    n = min(per_core * cores, llr.shape[0])
+    sample = llr[:n].cpu().numpy().astype(np.float64)
+    g_hard = hard[:n].cpu().numpy().view(np.uint32)
+    g_iters = iters[:n].cpu().numpy()
+    kind = "reference" if po.have_ref() else "port"
+    if kind == "reference":
+        with mp.get_context("fork").Pool(cores) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_decode_worker, [(sample[i::cores],) for i in range(cores)])
+            dt = time.perf_counter() - t0
+        r_hard = np.zeros((n, dec.N), np.uint8); r_iters = np.zeros(n, np.int32)
+        for i, (_, h, it) in enumerate(res):
+            r_hard[i::cores] = h; r_iters[i::cores] = it
+    else:
+        t0 = time.perf_counter()
+        r = po.orc_decode(DECODER, dec_hd(dec), Z, sample, MAXITER)
+        dt = time.perf_counter() - t0
+        r_hard, r_iters, cores = r["hard"], r["iters"], 1
+    bits = ((g_hard[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(n, -1)[:, :dec.N].astype(np.uint8)
+    bad = (g_iters != r_iters) | (bits != r_hard).any(axis=1)
+    return {"value": n * K / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "first %d frames of the same LLR buffers, reference lmin_sum_decod_qc_lm (early exit on, avg %.2f iters), "
+                      "one process per core" % (n, float(np.abs(r_iters).mean())),
+            "parity_mismatch_frames": int(bad.sum()), "parity_frames": int(n)}
+
+
+def dec_hd(dec):
+    from codes import load_code
+    return load_code(CODE)[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step (default 2^20 = config C2)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

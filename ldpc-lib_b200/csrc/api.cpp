@@ -146,7 +146,7 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
     bool use_fast = h->fast.ok && !(io.post && io.post_dtype != default_post_dtype(h->decoder_id, h->p.precision));
     if (use_fast && h->decoder_id == LDPCB200_LMS_DEC) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);
-        CU(launch_lms_fast(h->fast, h->gd, io, std::max(fgrid, 1), h->stream));
+        CU(launch_lms_fast(h->fast, io, std::max(fgrid, 1), h->stream));
     } else if (use_fast && h->decoder_id == LDPCB200_IMS_DEC) {
         CU(h->coef.reserve(sizeof(double) * (size_t)std::max(io.nf, 1)));
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);

@@ -55,8 +55,9 @@ struct LmsGeneric {
         int parity = syndrome_neg(g, soft);             // :5111-5115
         int ret = 0, locked = 0, iter;
         const bool noexit = io.flags & LDPCB200_NO_EARLY_EXIT;
+        if (!parity) { ret = 1; locked = 1; }           // already a codeword: 0 + 1
         for (iter = 0; iter < io.maxiter; iter++) {
-            if (!parity) { if (!locked) { ret = iter + 1; locked = 1; } if (!noexit) break; }
+            if (!parity && !noexit) break;              // :5119
             for (int j = 0; j < g.b; j++) {
                 const int e0 = g.rp[j], deg = g.rp[j + 1] - e0;
                 for (int n = tid; n < Z; n += nt) {
@@ -94,6 +95,7 @@ struct LmsGeneric {
                 __syncthreads();
             }
             parity = syndrome_neg(g, soft);             // :5281-5284
+            if (!parity && !locked) { ret = iter + 1; locked = 1; }
             if (!parity && !noexit) break;
         }
         if (!locked) ret = parity ? -iter : iter + 1;   // :5424

@@ -4,7 +4,7 @@
 
 namespace ldpcb200 {
 
-FastPlan plan_ims_fast(const QcHost&, const DecParams&, int, int) { FastPlan p{}; return p; }
+FastPlan plan_ims_fast(const QcHost&, const DecParams&, int, int) { return FastPlan(); }
 
 cudaError_t launch_ims_fast(const FastPlan&, const QcDev&, const DecParams&, const FrameIO&, double*, int, cudaStream_t)
 {

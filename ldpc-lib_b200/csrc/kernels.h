@@ -1,6 +1,7 @@
 // Internal interface between the C-ABI layer (api.cpp) and the CUDA translation units.
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "../../include/ldpcb200.h"
@@ -58,13 +59,14 @@ cudaError_t launch_generic(int decoder_id, int precision, const QcDev& g, const 
 
 // ---- shared-memory throughput kernels (lms_fast.cu, ims_fast.cu)
 struct FastPlan {
-    int ok;                     // 0: this (code, decoder, precision) has no fast kernel
-    int threads, frames_per_cta, ctas_per_sm;
-    size_t smem_bytes;
-    int variant;
+    int ok = 0;                 // 0: this (code, decoder, precision) has no fast kernel
+    int threads = 0, frames_per_cta = 1, ctas_per_sm = 1;
+    size_t smem_bytes = 0;
+    int variant = 0;
+    std::vector<unsigned char> tab;     // the kernel's parameter-space copy of the edge lists
 };
 FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block);
-cudaError_t launch_lms_fast(const FastPlan& p, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s);
+cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cudaStream_t s);
 FastPlan plan_ims_fast(const QcHost& g, const DecParams& dp, int smem_per_sm, int smem_per_block);
 cudaError_t launch_ims_fast(const FastPlan& p, const QcDev& g, const DecParams& dp, const FrameIO& io,
                             double* coef, int grid, cudaStream_t s);
