@@ -38,6 +38,8 @@ struct LmsTab {                     // lives in the kernel-parameter constant ba
     int b, c, Z, N, R, E, nwords;
     unsigned short rp[MAXB + 1];
     unsigned short thr4[MAXE];      // 4 * (Z - shift): lanes with 4n >= thr4 wrap
+    unsigned short sh[MAXE];        // shift
+    unsigned char col[MAXE];        // block column
     unsigned int rd[MAXE];          // byte offset of bit (col, shift) in soft2: 4 * (col * 2Z + shift)
 };
 
@@ -100,17 +102,40 @@ __device__ __forceinline__ void lms_layer_dispatch(const LmsTab& T, unsigned cha
     }
 }
 
-// parity of the hard decisions of every check row of this lane, OR-ed (check_syndrome, decoders.cpp:793-814)
-__device__ __forceinline__ unsigned lms_syndrome(const LmsTab& T, const unsigned char* sm, unsigned n4)
+// Syndrome of the hard decisions (check_syndrome, decoders.cpp:793-814) on packed bits.
+// Step 1: every warp packs the sign bits of 32 consecutive bits of each block column with one ballot
+// (hb[col * HW + w], HW = Zp / 32 words; bits >= Z of the last word are 0).  Step 2: one thread per (block
+// row, 32-lane block) XORs, edge by edge, the 32-bit window of the column's bit string that starts at
+// (32 w + shift) mod Z -- a funnel shift of two words, plus the wrap when the window crosses bit Z.
+// That is ~4 instructions per edge and 32 check rows instead of ~4 per edge and check row.
+__device__ __forceinline__ int lms_syndrome(const LmsTab& T, const float* soft2, unsigned* hb, int tid, int nt)
 {
-    unsigned bad = 0;
-    for (int j = 0; j < T.b; j++) {
-        unsigned x = 0;
-        const int e1 = T.rp[j + 1];
-        for (int e = T.rp[j]; e < e1; e++) x ^= __float_as_uint(lds_f(sm, T.rd[e] + n4));
-        bad |= x;
+    const int Z = T.Z, HW = nt >> 5, lane = tid & 31, warp = tid >> 5;
+    for (int col = 0; col < T.c; col++) {
+        const int bit = tid < Z ? soft2[col * 2 * Z + tid] < 0.0f : 0;
+        const unsigned w = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) hb[col * HW + warp] = w;
     }
-    return bad >> 31;
+    __syncthreads();
+    const int NB = (Z + 31) >> 5;
+    unsigned bad = 0;
+    for (int t = tid; t < T.b * NB; t += nt) {
+        const int j = t / NB, w = t - j * NB;
+        unsigned acc = 0;
+        for (int e = T.rp[j]; e < T.rp[j + 1]; e++) {
+            const unsigned* hc = hb + T.col[e] * HW;
+            int start = 32 * w + T.sh[e];
+            if (start >= Z) start -= Z;
+            unsigned win = __funnelshift_r(hc[start >> 5], hc[min((start >> 5) + 1, HW - 1)], start & 31);
+            const int nvalid = Z - start;
+            if (nvalid < 32) win = (win & ((1u << nvalid) - 1u)) | (hc[0] << nvalid);
+            acc ^= win;
+        }
+        const int lanes = Z - 32 * w;
+        if (lanes < 32) acc &= (1u << lanes) - 1u;
+        bad |= acc;
+    }
+    return __syncthreads_or(bad != 0);
 }
 
 __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ LmsTab T, const __grid_constant__ FrameIO io)
@@ -122,6 +147,8 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
     float* min2 = min1 + R;
     unsigned* ps = (unsigned*)(min2 + R);
     int* s_misc = (int*)(ps + R);                   // [0] next frame, [1] bit errors, [2] info-bit errors
+    unsigned* hb = (unsigned*)s_misc;               // packed hard decisions, c * nt / 32 words; aliases s_misc, which is
+                                                    // only live between frames (keeps two frames per SM at Z = 256)
     const bool active = tid < Z;
     const unsigned n4 = 4u * tid, Z4 = 4u * Z;
     const bool noexit = io.flags & LDPCB200_NO_EARLY_EXIT;
@@ -159,7 +186,7 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
         for (int i = tid; i < R; i += nt) { min1[i] = 0.0f; min2[i] = 0.0f; ps[i] = 0u; }
         __syncthreads();
 
-        int parity = __syncthreads_or(active ? (int)lms_syndrome(T, sm, n4) : 0);       // :5111-5115
+        int parity = lms_syndrome(T, soft2, hb, tid, nt);                               // :5111-5115
         int ret = 0, locked = 0, iter;
         if (!parity) { ret = 1; locked = 1; }                                           // already a codeword: 0 + 1
         for (iter = 0; iter < io.maxiter; iter++) {
@@ -169,7 +196,7 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
                 if (active) lms_layer_dispatch(T, sm, e0, deg, n4, Z4, min1, min2, ps, j * Z + tid);
                 __syncthreads();
             }
-            parity = __syncthreads_or(active ? (int)lms_syndrome(T, sm, n4) : 0);       // :5281-5284
+            parity = lms_syndrome(T, soft2, hb, tid, nt);                               // :5281-5284
             if (!parity && !locked) { ret = iter + 1; locked = 1; }
             if (!parity && !noexit) break;
         }
@@ -187,6 +214,9 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
                     for (int k = tid; k < Z; k += nt) p[col * Z + k] = (double)soft2[col * 2 * Z + k];
             }
         }
+        __syncthreads();
+        if (tid == 0) { s_misc[1] = 0; s_misc[2] = 0; }      // hb (aliased) is dead from here on
+        __syncthreads();
         {
             const int lane = tid & 31;
             int nerr = 0, nerr_info = 0;
@@ -225,7 +255,12 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
     }
 }
 
-size_t lms_fast_smem(const QcHost& g) { return (size_t)8 * g.N + (size_t)12 * g.R + 64; }
+size_t lms_fast_smem(const QcHost& g)
+{
+    const int zp = (g.Z + 31) & ~31;
+    const size_t hb = (size_t)4 * g.c * (zp / 32);
+    return (size_t)8 * g.N + (size_t)12 * g.R + (hb > 16 ? hb : 16);
+}
 
 } // namespace
 
@@ -253,6 +288,8 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
     for (int e = 0; e < g.E; e++) {
         T.thr4[e] = (unsigned short)(4 * (g.Z - g.sh[e]));
         T.rd[e] = 4u * (unsigned)(g.col[e] * 2 * g.Z + g.sh[e]);
+        T.sh[e] = (unsigned short)g.sh[e];
+        T.col[e] = (unsigned char)g.col[e];
     }
     return p;
 }
