@@ -1,0 +1,46 @@
+#include "commons.h"
+
+#include <random>
+
+int initial_random_seed = 0;
+static bool random_initialized = false;
+static unsigned long long noise_epoch = 0;
+
+void die(char const* format, ...)
+{
+    va_list ap;
+    va_start(ap, format);
+    vfprintf(stderr, format, ap);
+    va_end(ap);
+    fputs("\n", stderr);
+    exit(1);
+}
+
+std::string format_to_string(char const* format, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, format);
+    vsnprintf(buf, sizeof buf, format, ap);
+    va_end(ap);
+    return buf;
+}
+
+void reset_random()
+{
+    random_initialized = false;
+    ++noise_epoch;
+}
+
+void ensure_random_is_initialized()
+{
+    if (random_initialized) return;
+    if (initial_random_seed == 0) {
+        std::random_device device;
+        initial_random_seed = (int)device();
+        if (initial_random_seed == 0) initial_random_seed = 1;
+    }
+    random_initialized = true;
+}
+
+unsigned long long current_noise_epoch() { return noise_epoch; }

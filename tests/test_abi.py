@@ -1,0 +1,98 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/ldpcb200.h declares, and every compute
+entry point refuses to run without a CUDA device (there is no CPU fallback in the product)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_binding
+
+HEADER = os.path.join(ROOT, "include", "ldpcb200.h")
+
+
+def declared_symbols():
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(ldpcb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = load_binding().lib()
+    names = declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "ldpcb200.h"\nint main(void){ ldpcb200_params p; ldpcb200_sim_params s; ldpcb200_counters c; (void)p;(void)s;(void)c; return LDPCB200_VERSION > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_struct_layouts_match_binding():
+    """ctypes mirrors of the ABI structs have the sizes the C compiler gives them."""
+    L = load_binding()
+    prog = r'''
+#include <stdio.h>
+#include "ldpcb200.h"
+int main(void){ printf("%zu %zu %zu\n", sizeof(ldpcb200_params), sizeof(ldpcb200_sim_params), sizeof(ldpcb200_counters)); return 0; }
+'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [C.sizeof(L.Params), C.sizeof(L.SimParams), C.sizeof(L.Counters)]
+
+
+def test_sigma_is_host_arithmetic():
+    L = load_binding()
+    assert L.sigma(16, 32, 0, 2.0) == pytest.approx(np.sqrt(10 ** -0.2 / 2 / 0.5))
+    assert L.sigma(46, 68, 2, 2.0, L.MOD_QAM64) == pytest.approx(np.sqrt(10 ** -0.2 / (2 * (22 / 66) * 3 * 2) * 42.0))
+    assert L.lib().ldpcb200_version() >= 100
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="a GPU is present")
+def test_no_cpu_fallback_without_a_device():
+    L = load_binding()
+    hd = np.zeros((2, 4), np.int16)
+    with pytest.raises(L.LdpcError) as e:
+        L.Decoder(hd, 8, L.LMS_DEC)
+    assert e.value.code == L.ENODEV
+    with pytest.raises(L.LdpcError) as e:
+        L.demodulate(16, 4, 0.5, np.zeros(8))
+    assert e.value.code == L.ENODEV
+
+
+def test_argument_validation_comes_before_the_device():
+    L = load_binding()
+    hd = np.zeros((2, 4), np.int16)
+    with pytest.raises(L.LdpcError) as e:
+        L.Decoder(hd, 8, 6)                        # FHT_DEC: GF(q), out of scope
+    assert e.value.code == L.EINVAL
+    with pytest.raises(L.LdpcError) as e:
+        L.Decoder(hd, 8, L.TASP_DEC, precision=32)
+    assert e.value.code in (L.EUNSUPPORTED, L.ENODEV)
+
+
+def test_product_does_not_reference_the_oracle():
+    """Nothing under ldpc-lib_b200/ may include, link or load anything under oracle/."""
+    pkg = os.path.join(ROOT, "ldpc-lib_b200")
+    for base, _, files in os.walk(pkg):
+        if os.sep + "build" in base or os.sep + "bin" in base:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")) or f == "Makefile":
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "ldpc_oracle" not in txt and "pyoracle" not in txt and "libldpcref" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
