@@ -1,5 +1,6 @@
 // Stand-alone channel / utility kernels (see channel.cuh for the device functions they share with the
 // decoders' fused first load).
+#include "kernels.h"
 #include "channel.cuh"
 
 namespace ldpcb200 {

@@ -13,23 +13,22 @@
 //   Philox4x32-10(key = seed, counter = (i / 4, f_lo, f_hi, stream))[i % 4]  ->  Box-Muller (fp32),
 // which makes results independent of batch size, launch geometry and GPU count.
 #pragma once
-#include <cstdint>
-#include "kernels.h"
+#include "frame_io.h"
 
 namespace ldpcb200 {
 
-struct u32x4 { uint32_t x, y, z, w; };
+struct u32x4 { unsigned int x, y, z, w; };
 
-__host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                        uint32_t k0, uint32_t k1)
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                                                        unsigned int k0, unsigned int k1)
 {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    const unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int r = 0; r < 10; r++) {
         unsigned long long p0 = (unsigned long long)M0 * c0, p1 = (unsigned long long)M1 * c2;
-        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        unsigned int hi0 = (unsigned int)(p0 >> 32), lo0 = (unsigned int)p0, hi1 = (unsigned int)(p1 >> 32), lo1 = (unsigned int)p1;
         c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
         k0 += W0; k1 += W1;
     }
@@ -39,7 +38,7 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1
 
 #ifdef __CUDACC__
 // two N(0,1) samples from two 32-bit words
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1)
+__device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, float& z0, float& z1)
 {
     float u = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) / 2^32
     float r = sqrtf(__fmul_rn(-2.0f, logf(u)));
@@ -50,20 +49,20 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 }
 
 // noise sample `idx` of frame `frame`
-__device__ __forceinline__ float channel_noise(const ChannelParams& ch, unsigned long long frame, uint32_t idx)
+__device__ __forceinline__ float channel_noise(const ChannelParams& ch, unsigned long long frame, unsigned int idx)
 {
-    u32x4 w = philox4x32_10(idx >> 2, (uint32_t)frame, (uint32_t)(frame >> 32), ch.stream,
-                            (uint32_t)ch.seed, (uint32_t)(ch.seed >> 32));
+    u32x4 w = philox4x32_10(idx >> 2, (unsigned int)frame, (unsigned int)(frame >> 32), ch.stream,
+                            (unsigned int)ch.seed, (unsigned int)(ch.seed >> 32));
     float z0, z1;
     if (idx & 2) box_muller(w.z, w.w, z0, z1); else box_muller(w.x, w.y, z0, z1);
     return (idx & 1) ? z1 : z0;
 }
 
 // four consecutive noise samples idx4*4 .. idx4*4+3
-__device__ __forceinline__ void channel_noise4(const ChannelParams& ch, unsigned long long frame, uint32_t idx4, float z[4])
+__device__ __forceinline__ void channel_noise4(const ChannelParams& ch, unsigned long long frame, unsigned int idx4, float z[4])
 {
-    u32x4 w = philox4x32_10(idx4, (uint32_t)frame, (uint32_t)(frame >> 32), ch.stream,
-                            (uint32_t)ch.seed, (uint32_t)(ch.seed >> 32));
+    u32x4 w = philox4x32_10(idx4, (unsigned int)frame, (unsigned int)(frame >> 32), ch.stream,
+                            (unsigned int)ch.seed, (unsigned int)(ch.seed >> 32));
     box_muller(w.x, w.y, z[0], z[1]);
     box_muller(w.z, w.w, z[2], z[3]);
 }
@@ -130,7 +129,7 @@ static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, un
     int sym = i / ch.m, r = i - sym * ch.m;
     int comp = r >= half;
     int bit = r - comp * half;
-    float nz = channel_noise(ch, frame, (uint32_t)(2 * sym + comp));
+    float nz = channel_noise(ch, frame, (unsigned int)(2 * sym + comp));
     // all-zero bits -> natural index 0 -> gray[0] = 0 -> coordinate -(sqrt(Q) - 1)  (QAM_modulator.cpp:127-140)
     double x = (double)nz * ch.sigma_d - (double)((1 << half) - 1);
     double o[4];
@@ -142,7 +141,7 @@ static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, un
 __device__ __forceinline__ float channel_llr(const ChannelParams& ch, unsigned long long frame, int i)
 {
     if (i >= ch.punct_start) return ch.punct_value;
-    if (ch.m <= 2) return bpsk_llr(ch, channel_noise(ch, frame, (uint32_t)i));
+    if (ch.m <= 2) return bpsk_llr(ch, channel_noise(ch, frame, (unsigned int)i));
     return channel_llr_qam(ch, frame, i);
 }
 #endif

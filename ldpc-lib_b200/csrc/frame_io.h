@@ -1,0 +1,43 @@
+// Plain-old-data structures shared by the host code, the ahead-of-time kernels and the run-time compiled
+// (NVRTC) code-specialised kernels.  No includes and only built-in types, so that NVRTC can compile it as is.
+#pragma once
+
+namespace ldpcb200 {
+
+// Channel description for on-device LLR generation (bp_simulation.cpp:444-449, 600-630).
+struct ChannelParams {
+    int enabled;                // 0: LLRs come from FrameIO::llr
+    int modulation;             // enum ldpcb200_modulation
+    int m;                      // bits per QAM symbol (1 for BPSK)
+    float sigma;                // sigma (BPSK) or sigmaQAM
+    float llr_scale;            // 2 / sigma^2
+    double sigma_d;             // the same in double for the Demodulate arithmetic
+    double T;                   // Demodulate clip
+    int punct_start;            // first punctured bit (N if none)
+    float punct_value;          // 0.5 for LLR-domain decoders, 0 otherwise (bp_simulation.cpp:700)
+    unsigned long long seed;
+    unsigned int stream;
+    unsigned long long first_frame;
+};
+
+// Everything one decode launch reads and writes (all pointers are device pointers).
+struct FrameIO {
+    const void* llr;            // nf*N values of llr_dtype (F64 | F32); unused when ch.enabled
+    int llr_dtype;
+    int nf;
+    int maxiter;
+    unsigned int flags;
+    unsigned int* hard_words;       // nf * nwords packed decisions (may be null)
+    int* iters;             // nf (may be null)
+    void* post;                 // nf*N of post_dtype (may be null)
+    int post_dtype;
+    short* aux;               // IMS: ims_y (may be null)
+    unsigned int* per_frame;        // nf error records (may be null)
+    unsigned long long* counters;   // 6 x u64 (may be null): frames, frame_errors, info_bit_errors,
+                                    // undetected, iter_sum, bit_errors
+    unsigned char* bp_syndrome;       // R bytes: BP_DEC chained syndrome (decoders.cpp:1742-1759), or null
+    unsigned int* next_frame;   // work counter of the persistent grid (zeroed before the launch)
+    ChannelParams ch;
+};
+
+} // namespace ldpcb200

@@ -6,44 +6,9 @@
 
 #include "../../include/ldpcb200.h"
 #include "qc_layout.h"
+#include "frame_io.h"
 
 namespace ldpcb200 {
-
-// Channel description for on-device LLR generation (bp_simulation.cpp:444-449, 600-630).
-struct ChannelParams {
-    int enabled;                // 0: LLRs come from FrameIO::llr
-    int modulation;             // enum ldpcb200_modulation
-    int m;                      // bits per QAM symbol (1 for BPSK)
-    float sigma;                // sigma (BPSK) or sigmaQAM
-    float llr_scale;            // 2 / sigma^2
-    double sigma_d;             // the same in double for the Demodulate arithmetic
-    double T;                   // Demodulate clip
-    int punct_start;            // first punctured bit (N if none)
-    float punct_value;          // 0.5 for LLR-domain decoders, 0 otherwise (bp_simulation.cpp:700)
-    unsigned long long seed;
-    unsigned int stream;
-    unsigned long long first_frame;
-};
-
-// Everything one decode launch reads and writes (all pointers are device pointers).
-struct FrameIO {
-    const void* llr;            // nf*N values of llr_dtype (F64 | F32); unused when ch.enabled
-    int llr_dtype;
-    int nf;
-    int maxiter;
-    uint32_t flags;
-    uint32_t* hard_words;       // nf * nwords packed decisions (may be null)
-    int32_t* iters;             // nf (may be null)
-    void* post;                 // nf*N of post_dtype (may be null)
-    int post_dtype;
-    int16_t* aux;               // IMS: ims_y (may be null)
-    uint32_t* per_frame;        // nf error records (may be null)
-    unsigned long long* counters;   // 6 x u64 (may be null): frames, frame_errors, info_bit_errors,
-                                    // undetected, iter_sum, bit_errors
-    uint8_t* bp_syndrome;       // R bytes: BP_DEC chained syndrome (decoders.cpp:1742-1759), or null
-    unsigned int* next_frame;   // work counter of the persistent grid (zeroed before the launch)
-    ChannelParams ch;
-};
 
 struct DecParams {
     double alpha, thr;
@@ -62,7 +27,8 @@ struct FastPlan {
     int ok = 0;                 // 0: this (code, decoder, precision) has no fast kernel
     int threads = 0, frames_per_cta = 1, ctas_per_sm = 1;
     size_t smem_bytes = 0;
-    int variant = 0;
+    int variant = 0;                    // 0 table-driven (lms_fast.cu), 1 code-specialised ahead of time, 2 run-time compiled
+    int spec_index = -1;
     std::vector<unsigned char> tab;     // the kernel's parameter-space copy of the edge lists
 };
 FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block);

@@ -23,6 +23,7 @@
 // at 0 and the 32767 ceiling (decoders.cpp:5131-5168, 4301) are applied once per row; the position of
 // the minimum is only ever used to choose between min1 and min2, which are equal whenever the
 // reference's first-minimum tie rule (:5012-5027) could pick a different edge.
+#include <cstdlib>
 #include "kernels.h"
 #include "channel.cuh"
 
@@ -264,10 +265,24 @@ size_t lms_fast_smem(const QcHost& g)
 
 } // namespace
 
+int find_lms_spec_aot(const QcHost& g);
+void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size_t* smem);
+cudaError_t launch_lms_spec_aot(int idx, const FrameIO& io, int grid, cudaStream_t s);
+
 FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block)
 {
     FastPlan p;
     if (precision != 32) return p;                          // the double path stays on the bit-exact table-driven kernel
+    const char* no_spec = getenv("LDPCB200_NO_SPEC");
+    const int aot = (no_spec && *no_spec == '1') ? -1 : find_lms_spec_aot(g);
+    if (aot >= 0) {                                          // a code-specialised instance exists for this matrix
+        int minb = 1;
+        lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);
+        if (p.smem_bytes <= (size_t)smem_per_block) {
+            p.ok = 1; p.variant = 1; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.spec_index = aot;
+            return p;
+        }
+    }
     if (g.E > MAXE || g.b > MAXB || g.maxdeg > MAXDEG_FAST || g.Z > 512) return p;
     const size_t smem = lms_fast_smem(g);
     if (smem > (size_t)smem_per_block) return p;
@@ -296,6 +311,7 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
 
 cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cudaStream_t s)
 {
+    if (p.variant == 1) return launch_lms_spec_aot(p.spec_index, io, grid, s);
     const LmsTab& T = *reinterpret_cast<const LmsTab*>(p.tab.data());
     cudaError_t e = cudaFuncSetAttribute(lms_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;

@@ -1,0 +1,250 @@
+// Code-specialised LMS_DEC kernel (fp32): the same arithmetic as lms_fast.cu (bit-identical results), with the
+// base matrix baked in at compile time.  It is compiled once per code -- ahead of time for the frozen benchmark
+// matrices (lms_spec_aot.cu), at run time through NVRTC for any other code (spec_jit.cpp) -- from a generated
+//
+//   struct Code { static constexpr int B, C, Z, E, ZP, MINB;                 // ZP = threads, MINB = CTAs per SM
+//                 static constexpr int RP[B + 1], COL[E], SH[E];             // compile-time copies
+//                 static const int* rt_rp() / rt_col() / rt_sh(); };         // __constant__ copies for run-time indexing
+//
+// What specialisation buys over the table-driven kernel: every layer is unrolled, so (1) the soft-value address
+// of an edge is `lane + immediate` (no table loads, no index arithmetic; the mirror store of the doubled column
+// is two predicated stores with immediate offsets), (2) the check-row state (min1, min2, signs|pos) of all B
+// block rows of a lane lives in REGISTERS across iterations -- shared memory holds only the doubled posteriors,
+// 8N bytes per frame (64 KB at N = 8192 -> 3 frames per SM instead of 2), and (3) the position compare is
+// against an immediate.  This header must stay free of #include (NVRTC compiles it as one string together with
+// frame_io.h and channel.cuh).
+#pragma once
+
+namespace ldpcb200 {
+
+template <class K>
+struct LmsSpec {
+    static constexpr int B = K::B, C = K::C, Z = K::Z, N = K::C * K::Z, R = K::B * K::Z, ZP = K::ZP;
+    static constexpr int HW = ZP / 32;                       // words per block column of the packed decisions
+    static constexpr int NB = (Z + 31) / 32;
+    static constexpr int NWORDS = (N + 31) / 32;
+    static constexpr bool ALL_ACTIVE = (Z == ZP);
+    static constexpr int SMEM_WORDS = 2 * N + (C * HW > 4 ? C * HW : 4);
+
+    // ---- one block row J of one lane.  The edge loops are compile-time recursions so that every per-edge
+    // constant (K::COL, K::SH) is used in a constant expression: the tables never exist in device memory.
+    struct RowAcc { float c1, c2; unsigned sacc; };
+
+    template <int J, int Q>
+    static __device__ __forceinline__ void phase1(const float* soft2, int n, float pm1, float pm2, unsigned pps, unsigned ppos,
+                                                  float (&v)[K::RP[J + 1] - K::RP[J]], RowAcc& a)
+    {
+        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q < DEG) {
+            constexpr int off = K::COL[E0 + Q] * 2 * Z + K::SH[E0 + Q];
+            const float sv = soft2[n + off];
+            const float pabs = ppos == (unsigned)Q ? pm2 : pm1;                              // decoders.cpp:5152
+            const float pval = __uint_as_float(__float_as_uint(pabs) ^ ((pps << Q) & 0x80000000u));   // :5156
+            const float vv = sv - pval;                                                      // :5158
+            v[Q] = vv;
+            a.sacc ^= __float_as_uint(vv);
+            const float x = fabsf(vv);
+            a.c2 = fminf(a.c2, fmaxf(a.c1, x));                                              // :5012-5027
+            a.c1 = fminf(a.c1, x);
+            phase1<J, Q + 1>(soft2, n, pm1, pm2, pps, ppos, v, a);
+        }
+    }
+
+    template <int J, int Q>
+    static __device__ __forceinline__ void phase2(float* soft2, int n, const float (&v)[K::RP[J + 1] - K::RP[J]], float c1,
+                                                  unsigned m1x, unsigned m2x, unsigned& S, unsigned& pos)
+    {
+        constexpr int E0 = K::RP[J];
+        if constexpr (Q >= 0) {
+            constexpr int sh = K::SH[E0 + Q];
+            constexpr int off = K::COL[E0 + Q] * 2 * Z + sh;
+            const bool ismin = fabsf(v[Q]) == c1;
+            pos = ismin ? (unsigned)Q : pos;                                                 // reverse scan: the first minimum wins
+            const unsigned cv = (ismin ? m2x : m1x) ^ (__float_as_uint(v[Q]) & 0x80000000u); // :5193-5198
+            S = (S >> 1) | (cv & 0x80000000u);
+            const float nv = v[Q] + __uint_as_float(cv);                                     // :5199-5204
+            soft2[n + off] = nv;
+            if constexpr (sh == 0) soft2[n + off + Z] = nv;                                  // a zero shift never wraps
+            else {
+                if (n >= Z - sh) soft2[n + off - Z] = nv;
+                else soft2[n + off + Z] = nv;
+            }
+            phase2<J, Q - 1>(soft2, n, v, c1, m1x, m2x, S, pos);
+        }
+    }
+
+    template <int J>
+    static __device__ __forceinline__ void layer(float* soft2, int n, float& m1, float& m2, unsigned& ps)
+    {
+        constexpr int DEG = K::RP[J + 1] - K::RP[J];
+        float v[DEG];
+        RowAcc a;
+        a.c1 = __int_as_float(0x7f800000); a.c2 = a.c1; a.sacc = 0;
+        phase1<J, 0>(soft2, n, m1, m2, ps, ps & 0xffu, v, a);
+        const float n1 = fminf(fmaxf(a.c1 - 0.4f, 0.0f), 32767.0f);                          // :5166-5168, :5131-5137
+        const float n2 = fminf(fmaxf(a.c2 - 0.4f, 0.0f), 32767.0f);
+        const unsigned rs = a.sacc & 0x80000000u;
+        unsigned S = 0, pos = 0;
+        phase2<J, DEG - 1>(soft2, n, v, a.c1, __float_as_uint(n1) ^ rs, __float_as_uint(n2) ^ rs, S, pos);
+        m1 = n1; m2 = n2; ps = S | pos;                                                      // :5179
+    }
+
+    template <int J>
+    static __device__ __forceinline__ void layers(float* soft2, int n, bool active, float (&m1)[B], float (&m2)[B], unsigned (&ps)[B])
+    {
+        if constexpr (J < B) {
+            if (ALL_ACTIVE || active) layer<J>(soft2, n, m1[J], m2[J], ps[J]);
+            __syncthreads();
+            layers<J + 1>(soft2, n, active, m1, m2, ps);
+        }
+    }
+
+    // syndrome of the hard decisions on packed bits (see lms_fast.cu)
+    static __device__ __forceinline__ int syndrome(const float* soft2, unsigned* hb, int tid)
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll 4
+        for (int col = 0; col < C; col++) {
+            const int bit = (ALL_ACTIVE || tid < Z) ? soft2[col * 2 * Z + tid] < 0.0f : 0;
+            const unsigned w = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) hb[col * HW + warp] = w;
+        }
+        __syncthreads();
+        unsigned bad = 0;
+        for (int t = tid; t < B * NB; t += ZP) {
+            const int j = t / NB, w = t - j * NB;
+            unsigned acc = 0;
+            const int* rp = K::rt_rp();
+            const int* rcol = K::rt_col();
+            const int* rsh = K::rt_sh();
+            for (int e = rp[j]; e < rp[j + 1]; e++) {
+                const unsigned* hc = hb + rcol[e] * HW;
+                int start = 32 * w + rsh[e];
+                if (start >= Z) start -= Z;
+                const int i0 = start >> 5, i1 = i0 + 1 < HW ? i0 + 1 : HW - 1;
+                unsigned win = __funnelshift_r(hc[i0], hc[i1], start & 31);
+                const int nvalid = Z - start;
+                if (nvalid < 32) win = (win & ((1u << nvalid) - 1u)) | (hc[0] << nvalid);
+                acc ^= win;
+            }
+            const int lanes = Z - 32 * w;
+            if (lanes < 32) acc &= (1u << lanes) - 1u;
+            bad |= acc;
+        }
+        return __syncthreads_or(bad != 0);
+    }
+
+    static __device__ __forceinline__ void kernel(const FrameIO& io)
+    {
+        extern __shared__ __align__(16) float soft2[];
+        unsigned* hb = (unsigned*)(soft2 + 2 * N);
+        int* s_misc = (int*)hb;                                  // aliases hb: only live between frames
+        const int tid = threadIdx.x;
+        const bool active = tid < Z;
+        const bool noexit = io.flags & 8u;                       // LDPCB200_NO_EARLY_EXIT
+        float m1[B], m2[B];
+        unsigned ps[B];
+
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) { s_misc[0] = (int)atomicAdd(io.next_frame, 1u); s_misc[1] = 0; s_misc[2] = 0; }
+            __syncthreads();
+            const int f = s_misc[0];
+            if (f >= io.nf) break;
+
+            if (io.ch.enabled) {
+                const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
+                for (int i = tid; i < N; i += ZP) {
+                    const int col = i / Z, k = i - col * Z;
+                    const float x = channel_llr(io.ch, frame, i);
+                    soft2[col * 2 * Z + k] = x; soft2[col * 2 * Z + Z + k] = x;
+                }
+            } else if (io.llr_dtype == 1) {                      // LDPCB200_F32
+                const float* y = (const float*)io.llr + (size_t)f * N;
+                if (ALL_ACTIVE || active) {
+#pragma unroll 8
+                    for (int col = 0; col < C; col++) {
+                        const float x = __ldcs(y + col * Z + tid);
+                        soft2[col * 2 * Z + tid] = x; soft2[col * 2 * Z + Z + tid] = x;
+                    }
+                }
+            } else {
+                const double* y = (const double*)io.llr + (size_t)f * N;
+                if (ALL_ACTIVE || active) {
+#pragma unroll 8
+                    for (int col = 0; col < C; col++) {
+                        const float x = (float)__ldcs(y + col * Z + tid);
+                        soft2[col * 2 * Z + tid] = x; soft2[col * 2 * Z + Z + tid] = x;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < B; j++) { m1[j] = 0.0f; m2[j] = 0.0f; ps[j] = 0u; }     // decoders.cpp:5088-5108
+            __syncthreads();
+
+            int parity = syndrome(soft2, hb, tid);                                      // :5111-5115
+            int ret = 0, locked = 0, iter;
+            if (!parity) { ret = 1; locked = 1; }
+            for (iter = 0; iter < io.maxiter; iter++) {
+                if (!parity && !noexit) break;                                          // :5119
+                layers<0>(soft2, tid, active, m1, m2, ps);
+                parity = syndrome(soft2, hb, tid);                                      // :5281-5284
+                if (!parity && !locked) { ret = iter + 1; locked = 1; }
+                if (!parity && !noexit) break;
+            }
+            if (!locked) ret = parity ? -iter : iter + 1;                               // :5424
+
+            if (io.post) {
+                if (io.post_dtype == 1) {
+                    float* p = (float*)io.post + (size_t)f * N;
+                    for (int col = 0; col < C; col++)
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = soft2[col * 2 * Z + tid];
+                } else {
+                    double* p = (double*)io.post + (size_t)f * N;
+                    for (int col = 0; col < C; col++)
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = (double)soft2[col * 2 * Z + tid];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { s_misc[1] = 0; s_misc[2] = 0; }
+            __syncthreads();
+            {
+                const int lane = tid & 31;
+                int nerr = 0, nerr_info = 0;
+                constexpr int NROUND = (N + 31) & ~31;
+                for (int i = tid; i < NROUND; i += ZP) {
+                    int bit = 0;
+                    if (i < N) { const int col = i / Z, k = i - col * Z; bit = soft2[col * 2 * Z + k] < 0.0f; }   // :5421
+                    const unsigned w = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0) {
+                        if (io.hard_words) io.hard_words[(size_t)f * NWORDS + (i >> 5)] = w;
+                        nerr += __popc(w);
+                        const int lo = R - i;                    // bits >= R are information bits (bp_simulation.cpp:738)
+                        const unsigned wi = lo <= 0 ? w : (lo >= 32 ? 0u : (w >> lo) << lo);
+                        nerr_info += __popc(wi);
+                    }
+                }
+                if (lane == 0 && nerr) { atomicAdd(&s_misc[1], nerr); atomicAdd(&s_misc[2], nerr_info); }
+                __syncthreads();
+                if (tid == 0) {
+                    const int e = s_misc[1], ei = s_misc[2];
+                    if (io.iters) io.iters[f] = ret;
+                    if (io.per_frame)
+                        io.per_frame[f] = (e ? 0x80000000u : 0u) | (ret >= 0 ? 0x40000000u : 0u) | (unsigned)(ei < 0xFFFFFF ? ei : 0xFFFFFF);
+                    if (io.counters) {
+                        atomicAdd(&io.counters[0], 1ull);
+                        atomicAdd(&io.counters[4], (unsigned long long)(ret < 0 ? -ret : ret));
+                        if (e) {
+                            atomicAdd(&io.counters[1], 1ull);
+                            atomicAdd(&io.counters[2], (unsigned long long)ei);
+                            atomicAdd(&io.counters[5], (unsigned long long)e);
+                            if (ret >= 0) atomicAdd(&io.counters[3], 1ull);
+                        }
+                    }
+                }
+            }
+        }
+    }
+};
+
+} // namespace ldpcb200

@@ -1,0 +1,77 @@
+// Ahead-of-time instances of the code-specialised LMS_DEC kernel (lms_spec.cuh) for the frozen benchmark
+// matrices, generated at build time by tools/gen_lms_spec.py into build/lms_spec_aot_gen.h.  A handle whose
+// base matrix and lifting size match one of them runs it; every other code goes to the run-time compiled
+// instance (spec_jit.cpp) or, failing that, to the table-driven kernel of lms_fast.cu.
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+#include "channel.cuh"
+#include "lms_spec.cuh"
+
+namespace ldpcb200 {
+
+struct SpecEntry {
+    const char* name;
+    const void* kernel;
+    int b, c, Z, E, zp, minb;
+    const int *rp, *col, *sh;       // host copies for matching
+};
+
+static std::vector<SpecEntry>& registry()
+{
+    static std::vector<SpecEntry> r;
+    return r;
+}
+
+struct SpecRegistrar {
+    SpecRegistrar(const SpecEntry& e) { registry().push_back(e); }
+};
+
+} // namespace ldpcb200
+
+#define LDPC_SPEC_REGISTER(NAME, B_, C_, Z_, E_, ZP_, MINB_)                                                   \
+    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)lms_spec_##NAME, B_, C_, Z_, E_, ZP_, MINB_, \
+        ldpcb200::gen_##NAME::Code::RP, ldpcb200::gen_##NAME::Code::COL, ldpcb200::gen_##NAME::Code::SH});
+
+#include "lms_spec_aot_gen.h"
+
+namespace ldpcb200 {
+
+// -> index of the matching ahead-of-time instance, or -1
+int find_lms_spec_aot(const QcHost& g)
+{
+    const std::vector<SpecEntry>& r = registry();
+    for (size_t k = 0; k < r.size(); k++) {
+        const SpecEntry& e = r[k];
+        if (e.b != g.b || e.c != g.c || e.Z != g.Z || e.E != g.E) continue;
+        bool same = true;
+        for (int j = 0; j <= g.b && same; j++) same = e.rp[j] == g.rp[j];
+        for (int i = 0; i < g.E && same; i++) same = e.col[i] == g.col[i] && e.sh[i] == g.sh[i];
+        if (same) return (int)k;
+    }
+    return -1;
+}
+
+void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size_t* smem)
+{
+    const SpecEntry& e = registry()[idx];
+    const int hw = e.zp / 32;
+    if (name) *name = e.name;
+    if (threads) *threads = e.zp;
+    if (minb) *minb = e.minb;
+    if (smem) *smem = sizeof(float) * (2 * (size_t)e.c * e.Z + (e.c * hw > 4 ? e.c * hw : 4));
+}
+
+cudaError_t launch_lms_spec_aot(int idx, const FrameIO& io, int grid, cudaStream_t s)
+{
+    const SpecEntry& e = registry()[idx];
+    size_t smem;
+    lms_spec_aot_info(idx, nullptr, nullptr, nullptr, &smem);
+    cudaError_t err = cudaFuncSetAttribute(e.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    void* args[] = { (void*)&io };
+    return cudaLaunchKernel(e.kernel, dim3(grid), dim3(e.zp), args, smem, s);
+}
+
+} // namespace ldpcb200
