@@ -268,7 +268,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world, frames),
-                "kernel": dict(info, kernel_ms_per_step=kernel_ms, name="lms_fast_kernel" if info["fast"] else "generic_minsum_kernel"),
+                "kernel": dict(info, kernel_ms_per_step=kernel_ms),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": total_frames * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 72,
                         "d2h_bytes_per_step": 48 + 4 * frames, "gpu_launches": e2e_launches,

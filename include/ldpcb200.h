@@ -84,9 +84,12 @@ typedef struct {
                           bit-exact for LMS/MS) or 32 (LMS/MS only: same decisions and iteration
                           counts on >= 99.99 % of frames)                         */
     int    device;     /* CUDA device ordinal, -1 = current device                               */
-    int    use_fast;   /* 1 (default): the shared-memory throughput kernels where one exists
-                          (LMS_DEC, IMS_DEC) and the code fits; 0: the table-driven parity kernels
-                          only (one frame per CTA, state in an L2-resident workspace)            */
+    int    use_fast;   /* 0: the table-driven parity kernels only (one frame per CTA, state in an
+                          L2-resident workspace); 1 (default): the shared-memory throughput kernels
+                          where one exists (LMS_DEC) and the code fits, code-specialised when the
+                          matrix is one of the built-in benchmark matrices; 2: additionally compile a
+                          code-specialised kernel for THIS matrix at create time (NVRTC, a few
+                          seconds once per matrix and process; falls back to 1 if NVRTC is absent)  */
     int    reserved[8];
 } ldpcb200_params;
 
@@ -167,6 +170,10 @@ int ldpcb200_modulate(int Q, int ns, const uint8_t* bits, double* out, int devic
 
 /* sigma / sigmaQAM of bp_simulation.cpp:444-449 (host arithmetic, no device needed). */
 double ldpcb200_sigma(int b, int c, int punctured_blocks, double snr_db, int modulation);
+
+/* Diagnostic: generate and compile (NVRTC, no device needed) the code-specialised LMS_DEC kernel for a matrix
+ * and target architecture sm_<major><minor>; *cubin_bytes = size of the result. */
+int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int sm_minor, int* cubin_bytes);
 
 /* Kernel timing of the last decode_batch / simulate call on this handle, measured with CUDA events
  * on the handle's stream around the decode kernel launches only. */

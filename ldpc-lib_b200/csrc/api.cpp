@@ -20,6 +20,12 @@ cudaError_t launch_sumprod_generic(int decoder_id, const QcDev& g, const DecPara
                                    char* ws, size_t ws_stride, int grid, int nt, cudaStream_t s);
 }
 
+namespace ldpcb200 {
+bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem);
+std::string lms_spec_generate(const QcHost& g, int zp, int minb);
+bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<char>& cubin, std::string& why);
+}
+
 using namespace ldpcb200;
 
 namespace {
@@ -284,7 +290,7 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
         CU(h->bpsynd.reserve((size_t)h->g.R + 16));
         CU(cudaMemset(h->bpsynd.p, 0, (size_t)h->g.R + 16));
         if (p.use_fast) {
-            if (decoder_id == LDPCB200_LMS_DEC) h->fast = plan_lms_fast(h->g, p.precision, h->smem_per_sm, h->smem_per_block);
+            if (decoder_id == LDPCB200_LMS_DEC) h->fast = plan_lms_fast(h->g, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
             else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ims_fast(h->g, h->dp, h->smem_per_sm, h->smem_per_block);
         }
         return 0;
@@ -562,6 +568,20 @@ int ldpcb200_modulate(int Q, int ns, const uint8_t* bits, double* out, int devic
     if (e == cudaSuccess) e = cudaMemcpy(out, dout, sizeof(double) * 2 * ns, cudaMemcpyDeviceToHost);
     cudaFree(db); cudaFree(dout);
     if (e != cudaSuccess) return fail(LDPCB200_ECUDA, "modulate: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int sm_minor, int* cubin_bytes)
+{
+    QcHost g;
+    if (!g.build(hd, b, c, Z)) return fail(LDPCB200_EINVAL, "bad base matrix");
+    int zp, minb;
+    size_t smem;
+    if (!lms_spec_geometry(g, 233472, 232448, &zp, &minb, &smem)) return fail(LDPCB200_EUNSUPPORTED, "code does not suit the register-state kernel");
+    std::vector<char> cubin;
+    std::string why;
+    if (!lms_spec_compile(lms_spec_generate(g, zp, minb), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());
+    if (cubin_bytes) *cubin_bytes = (int)cubin.size();
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // Internal interface between the C-ABI layer (api.cpp) and the CUDA translation units.
 #pragma once
 #include <cstdint>
+#include <string>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -29,9 +30,11 @@ struct FastPlan {
     size_t smem_bytes = 0;
     int variant = 0;                    // 0 table-driven (lms_fast.cu), 1 code-specialised ahead of time, 2 run-time compiled
     int spec_index = -1;
+    const void* jit_kernel = nullptr;
+    std::string note;                   // why a faster variant was not used
     std::vector<unsigned char> tab;     // the kernel's parameter-space copy of the edge lists
 };
-FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block);
+FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block, int allow_jit);
 cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cudaStream_t s);
 FastPlan plan_ims_fast(const QcHost& g, const DecParams& dp, int smem_per_sm, int smem_per_block);
 cudaError_t launch_ims_fast(const FastPlan& p, const QcDev& g, const DecParams& dp, const FrameIO& io,

@@ -24,6 +24,8 @@
 // the minimum is only ever used to choose between min1 and min2, which are equal whenever the
 // reference's first-minimum tie rule (:5012-5027) could pick a different edge.
 #include <cstdlib>
+#include <algorithm>
+#include <string>
 #include "kernels.h"
 #include "channel.cuh"
 
@@ -269,7 +271,27 @@ int find_lms_spec_aot(const QcHost& g);
 void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size_t* smem);
 cudaError_t launch_lms_spec_aot(int idx, const FrameIO& io, int grid, cudaStream_t s);
 
-FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block)
+const void* lms_spec_jit(const QcHost& g, int zp, int minb, std::string& why);
+cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const FrameIO& io, int grid, cudaStream_t s);
+
+// launch geometry of the code-specialised kernel for g; false if the code does not suit it
+bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem)
+{
+    if (g.b > 32 || g.E > 512 || g.Z > 1024 || g.maxdeg > MAXDEG_FAST) return false;
+    *zp = (g.Z + 31) & ~31;
+    const int hw = *zp / 32;
+    *smem = sizeof(float) * (2 * (size_t)g.N + (g.c * hw > 4 ? g.c * hw : 4));
+    if (*smem > (size_t)smem_per_block) return false;
+    const int regs = 3 * g.b + 44;                           // check state of every block row + working set
+    int m = (int)((size_t)smem_per_sm / (*smem + 1024));
+    m = std::min(m, 2048 / *zp);
+    m = std::min(m, 65536 / (*zp * regs));
+    if (m < 1) return false;
+    *minb = std::min(m, 16);
+    return true;
+}
+
+FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block, int allow_jit)
 {
     FastPlan p;
     if (precision != 32) return p;                          // the double path stays on the bit-exact table-driven kernel
@@ -282,6 +304,21 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
             p.ok = 1; p.variant = 1; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.spec_index = aot;
             return p;
         }
+    }
+    if (allow_jit && !(no_spec && *no_spec == '1')) {       // compile one for this matrix
+        int zp, minb;
+        size_t smem;
+        if (lms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem)) {
+            std::string why;
+            const void* k = lms_spec_jit(g, zp, minb, why);
+            if (k) {
+                p.ok = 1; p.variant = 2; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem;
+                p.jit_kernel = k;
+                return p;
+            }
+            p.note = why;
+        } else
+            p.note = "code does not suit the register-state kernel (b > 32, too many edges, or shared memory)";
     }
     if (g.E > MAXE || g.b > MAXB || g.maxdeg > MAXDEG_FAST || g.Z > 512) return p;
     const size_t smem = lms_fast_smem(g);
@@ -312,6 +349,7 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
 cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cudaStream_t s)
 {
     if (p.variant == 1) return launch_lms_spec_aot(p.spec_index, io, grid, s);
+    if (p.variant == 2) return launch_lms_spec_jit(p.jit_kernel, p.threads, p.smem_bytes, io, grid, s);
     const LmsTab& T = *reinterpret_cast<const LmsTab*>(p.tab.data());
     cudaError_t e = cudaFuncSetAttribute(lms_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;

@@ -1,0 +1,159 @@
+// Run-time compilation of the code-specialised LMS_DEC kernel (lms_spec.cuh) for an arbitrary base matrix.
+//
+// The kernel text (frame_io.h + channel.cuh + lms_spec.cuh, embedded at build time as build/spec_src.inc) is
+// prefixed to a generated `Code` struct holding the matrix as compile-time tables, compiled with NVRTC for the
+// device's architecture (sm_100a on B200) and loaded through the CUDA runtime's library API.  NVRTC is opened
+// with dlopen, so the engine has no link-time dependency on it: when it is missing, or the compilation fails,
+// the caller is told and stays on the table-driven kernel (lms_fast.cu).  Compiled instances are cached per
+// process, keyed by the generated text, so an SNR sweep compiles once.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace ldpcb200 {
+
+namespace {
+
+const char* const KERNEL_TEXT =
+#include "spec_src.inc"
+    ;
+
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+    void* so = nullptr;
+    int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    bool ok = false;
+};
+
+Nvrtc& nvrtc()
+{
+    static Nvrtc n;
+    static bool tried = false;
+    if (tried) return n;
+    tried = true;
+    const char* names[] = { "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so" };
+    for (const char* nm : names)
+        if ((n.so = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!n.so) return n;
+#define SYM(f) *(void**)(&n.f) = dlsym(n.so, "nvrtc" #f)
+    SYM(CreateProgram); SYM(CompileProgram); SYM(GetCUBINSize); SYM(GetCUBIN); SYM(GetProgramLogSize); SYM(GetProgramLog); SYM(DestroyProgram);
+#undef SYM
+    n.ok = n.CreateProgram && n.CompileProgram && n.GetCUBINSize && n.GetCUBIN && n.GetProgramLogSize && n.GetProgramLog && n.DestroyProgram;
+    return n;
+}
+
+struct Compiled {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+};
+
+std::mutex g_mu;
+std::map<std::string, Compiled> g_cache;        // key: device ordinal + generated text
+
+template <class V>
+void put_array(std::ostringstream& o, const char* decl, const V& v, int n)
+{
+    o << decl << "[" << n << "] = { ";
+    for (int i = 0; i < n; i++) o << (i ? ", " : "") << v[i];
+    o << " };\n";
+}
+
+} // namespace
+
+// The generated part of the translation unit: same text as tools/gen_lms_spec.py writes for the ahead-of-time instances.
+std::string lms_spec_generate(const QcHost& g, int zp, int minb)
+{
+    std::ostringstream o;
+    o << "namespace ldpcb200 { namespace gen_jit {\n";
+    put_array(o, "__constant__ int RT_RP", g.rp, g.b + 1);
+    put_array(o, "__constant__ int RT_COL", g.col, g.E);
+    put_array(o, "__constant__ int RT_SH", g.sh, g.E);
+    o << "struct Code {\n";
+    o << "    static constexpr int B = " << g.b << ", C = " << g.c << ", Z = " << g.Z << ", E = " << g.E << ", ZP = " << zp << ", MINB = " << minb << ";\n";
+    put_array(o, "    static constexpr int RP", g.rp, g.b + 1);
+    put_array(o, "    static constexpr int COL", g.col, g.E);
+    put_array(o, "    static constexpr int SH", g.sh, g.E);
+    o << "    static __device__ __forceinline__ const int* rt_rp() { return RT_RP; }\n";
+    o << "    static __device__ __forceinline__ const int* rt_col() { return RT_COL; }\n";
+    o << "    static __device__ __forceinline__ const int* rt_sh() { return RT_SH; }\n";
+    o << "};\n} }\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") lms_spec_jit(const __grid_constant__ ldpcb200::FrameIO io)\n";
+    o << "{ ldpcb200::LmsSpec<ldpcb200::gen_jit::Code>::kernel(io); }\n";
+    return o.str();
+}
+
+// generated text -> cubin for sm_<major><minor>[a]; needs no device
+bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<char>& cubin, std::string& why)
+{
+    Nvrtc& n = nvrtc();
+    if (!n.ok) { why = "NVRTC (libnvrtc.so.12) not found"; return false; }
+    const std::string src = std::string(KERNEL_TEXT) + "\n" + gen;
+    nvrtcProgram prog = nullptr;
+    if (n.CreateProgram(&prog, src.c_str(), "lms_spec_jit.cu", 0, nullptr, nullptr) != 0) { why = "nvrtcCreateProgram failed"; return false; }
+    char arch[64];
+    // B200 is compute capability 10.0 -> sm_100a (architecture-specific features allowed)
+    snprintf(arch, sizeof arch, "--gpu-architecture=sm_%d%d%s", major, minor, major >= 9 ? "a" : "");
+    const char* opts[] = { arch, "--std=c++17", "-lineinfo", "-fmad=false" };
+    int rc = n.CompileProgram(prog, 4, opts);
+    if (rc != 0) {
+        size_t ls = 0;
+        n.GetProgramLogSize(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) n.GetProgramLog(prog, &log[0]);
+        why = "NVRTC compilation failed: " + log.substr(0, 2000);
+        n.DestroyProgram(&prog);
+        return false;
+    }
+    size_t cs = 0;
+    n.GetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    n.GetCUBIN(prog, cubin.data());
+    n.DestroyProgram(&prog);
+    return true;
+}
+
+// Compile (or fetch from the cache) the specialised kernel for `g` on the current device.
+// Returns nullptr and fills `why` when run-time compilation is not possible.
+const void* lms_spec_jit(const QcHost& g, int zp, int minb, std::string& why)
+{
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { why = "no device"; return nullptr; }
+    const std::string gen = lms_spec_generate(g, zp, minb);
+    const std::string key = std::to_string(dev) + "\n" + gen;
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) return (const void*)it->second.kernel;
+    std::vector<char> cubin;
+    if (!lms_spec_compile(gen, prop.major, prop.minor, cubin, why)) return nullptr;
+    Compiled c;
+    cudaError_t e = cudaLibraryLoadData(&c.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&c.kernel, c.lib, "lms_spec_jit");
+    if (e != cudaSuccess) { why = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
+    g_cache[key] = c;
+    return (const void*)c.kernel;
+}
+
+cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const FrameIO& io, int grid, cudaStream_t s)
+{
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    void* args[] = { (void*)&io };
+    return cudaLaunchKernel(kernel, dim3(grid), dim3(zp), args, smem, s);
+}
+
+} // namespace ldpcb200

@@ -90,6 +90,9 @@ std::pair<double, double> bp_simulation(
     // iteration counts as the double arithmetic on >= 99.99 % of frames); LDPCB200_PRECISION=64 forces double
     p.precision = (decoder_type == LMS_DEC || decoder_type == MS_DEC) ? 32 : 64;
     if (pe && atoi(pe) == 64) p.precision = 64;
+    // compile a code-specialised kernel for this matrix unless told not to (LDPCB200_JIT=0); cached per process
+    const char* je = getenv("LDPCB200_JIT");
+    p.use_fast = (je && atoi(je) == 0) ? 1 : 2;
     std::vector<ldpcb200_handle> eng;
     std::vector<int> devs = devices_from_env();
     for (size_t k = 0; k < devs.size(); k++) {

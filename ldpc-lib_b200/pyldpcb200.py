@@ -76,6 +76,7 @@ def lib():
         L.ldpcb200_generate_llr.argtypes = [C.c_void_p, C.POINTER(SimParams), C.c_void_p, C.c_int]
         L.ldpcb200_demodulate.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.ldpcb200_modulate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.ldpcb200_jit_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.ldpcb200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -142,7 +143,10 @@ class Decoder:
     def kernel_info(self):
         v = [C.c_int() for _ in range(5)]
         _check(lib().ldpcb200_kernel_info(self._h, *[C.byref(x) for x in v]))
-        return dict(zip(("fast", "threads", "frames_per_cta", "ctas_per_sm", "smem_bytes"), [x.value for x in v]))
+        d = dict(zip(("fast", "threads", "frames_per_cta", "ctas_per_sm", "smem_bytes"), [x.value for x in v]))
+        d["name"] = {0: "generic (table-driven, L2 workspace)", 1: "lms_fast_kernel (table-driven, shared memory)",
+                     2: "lms_spec (code-specialised, ahead of time)", 3: "lms_spec_jit (code-specialised, NVRTC)"}.get(d["fast"], "?")
+        return d
 
     def post_dtype(self):
         if self.decoder_id == IMS_DEC:
@@ -221,6 +225,14 @@ class Decoder:
 
     def stream(self):
         return lib().ldpcb200_stream(self._h)
+
+
+def jit_check(hd, Z, sm=(10, 0)):
+    """Generate + NVRTC-compile the code-specialised LMS_DEC kernel for a matrix (needs no GPU); -> cubin size."""
+    hd = np.ascontiguousarray(hd, dtype=np.int16)
+    n = C.c_int()
+    _check(lib().ldpcb200_jit_check(_ptr(hd), hd.shape[0], hd.shape[1], Z, sm[0], sm[1], C.byref(n)))
+    return n.value
 
 
 def demodulate(Q, ns, sigma_, x, T=26.0, out_type=0, device=-1):

@@ -96,3 +96,18 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py")) or f == "Makefile":
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "ldpc_oracle" not in txt and "pyoracle" not in txt and "libldpcref" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
+
+
+def test_code_specialised_kernel_generates_and_compiles_without_a_gpu():
+    """The run-time generator + NVRTC produce an sm_100a cubin for an arbitrary matrix (no device needed)."""
+    import shutil
+    if not (os.path.exists("/usr/local/cuda/lib64/libnvrtc.so.12") or shutil.which("nvcc")):
+        pytest.skip("NVRTC not installed")
+    from codes import load_code
+    L = load_binding()
+    hd, _ = load_code("c4_wifi_12x24")
+    assert L.jit_check(hd, 81) > 10000
+    hd3, _ = load_code("c3_bg1_46x68")
+    with pytest.raises(L.LdpcError) as e:                 # 46 block rows do not fit the register-state kernel
+        L.jit_check(hd3, 384)
+    assert e.value.code == L.EUNSUPPORTED

@@ -76,3 +76,24 @@ def test_simulate_matches_decode_on_generated_llr(ldpc, po):
     # the oracle agrees with the device decode of the same buffer
     want = po.orc_decode(po.LMS, hd, 256, llr, 10, dtype=np.float32)
     assert np.array_equal(dec["iters"], want["iters"]) and np.array_equal(dec["hard"], want["hard"])
+
+
+@pytest.mark.parametrize("code,Z,snr", [("c4_wifi_12x24", 81, 1.5), ("ref32x16_a", 126, 2.5)])
+def test_runtime_compiled_kernel_bit_exact(ldpc, po, code, Z, snr):
+    """use_fast = 2: the code-specialised kernel is generated and compiled (NVRTC) for a matrix that has no
+    ahead-of-time instance; same bit-identical results, incl. a lifting size that is not a multiple of 32."""
+    hd, llr = _case(code, Z, snr, 300)
+    llr = llr.astype(np.float32)
+    want = po.orc_decode(po.LMS, hd, Z, llr, 10, dtype=np.float32)
+    with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=2) as d:
+        assert d.kernel_info()["fast"] == 3, d.kernel_info()
+        got = d.decode(llr, 10, want_post=True)
+        sim = d.simulate(snr, 200, 10, seed=4, want_per_frame=True)
+        dec = d.decode(d.generate_llr(snr, 200, seed=4), 10)
+    assert np.array_equal(got["iters"], want["iters"])
+    assert np.array_equal(got["hard"], want["hard"])
+    assert np.array_equal(got["post"], want["post"])
+    assert sim["frame_errors"] == int((dec["hard"].sum(axis=1) > 0).sum())
+    with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=1) as d:
+        assert d.kernel_info()["fast"] == 1
+        assert np.array_equal(d.decode(llr, 10)["iters"], want["iters"])
