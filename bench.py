@@ -277,8 +277,13 @@ def run_ours(args):
                                "frame_failure_rate": fer_proxy},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame},
-                "issue": {"edge_updates_per_s": edge_updates, "thread_instr_peak_per_s": issue_peak,
-                          "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
+                # the binding roofline: min-sum is compare / select / logic work that issues on the
+                # ALU pipe (64 lanes / clk / SM); 13.9 ALU-pipe and 25.6 total SASS instructions per edge update
+                # (profiles/r01_lms_spec_v1_*: ncu source page and cuobjdump counts of the specialised kernel)
+                "issue": {"bound": "alu_pipe", "edge_updates_per_s": edge_updates, "alu_ops_per_edge_update": 13.9,
+                          "alu_lane_peak_per_s": 148 * 64 * sm_hz * 1e6,
+                          "frac": edge_updates * 13.9 / (148 * 64 * sm_hz * 1e6),
+                          "thread_instr_peak_per_s": issue_peak, "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(dec, llr, hard, iters, K)
         print(json.dumps(line))

@@ -277,7 +277,7 @@ cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const F
 // launch geometry of the code-specialised kernel for g; false if the code does not suit it
 bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem)
 {
-    if (g.b > 32 || g.E > 512 || g.Z > 1024 || g.maxdeg > MAXDEG_FAST) return false;
+    if (g.b > 32 || g.E > 512 || g.Z > 1024 || g.maxdeg > 16) return false;     // row word: 16 sign bits + 16 minimum flags
     *zp = (g.Z + 31) & ~31;
     const int hw = *zp / 32;
     *smem = sizeof(float) * (2 * (size_t)g.N + (g.c * hw > 4 ? g.c * hw : 4));

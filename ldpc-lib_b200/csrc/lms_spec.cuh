@@ -28,74 +28,117 @@ struct LmsSpec {
 
     // ---- one block row J of one lane.  The edge loops are compile-time recursions so that every per-edge
     // constant (K::COL, K::SH) is used in a constant expression: the tables never exist in device memory.
-    struct RowAcc { float c1, c2; unsigned sacc; };
+    // Row word ps: bit q = sign of the c2v message of edge q, bit 16 + q = "edge q carried the minimum" (row weight <= 16).
+    // With ties several edges carry the flag; their message min2 then equals min1, so the value is the reference's.
+    struct RowAcc { float c1, c2; };
+
+    // two smallest of {c1, c2, a, b}: order independent, exact (min / max only)
+    static __device__ __forceinline__ void track2(RowAcc& r, float a, float b)
+    {
+        const float lo = fminf(a, b), hi = fmaxf(a, b);
+        const float t = fmaxf(r.c1, lo);
+        r.c2 = fminf(fminf(r.c2, hi), t);
+        r.c1 = fminf(r.c1, lo);
+    }
+    static __device__ __forceinline__ void track1(RowAcc& r, float a)
+    {
+        r.c2 = fminf(r.c2, fmaxf(r.c1, a));                                                  // decoders.cpp:5012-5027
+        r.c1 = fminf(r.c1, a);
+    }
 
     template <int J, int Q>
-    static __device__ __forceinline__ void phase1(const float* soft2, int n, float pm1, float pm2, unsigned pps, unsigned ppos,
-                                                  float (&v)[K::RP[J + 1] - K::RP[J]], RowAcc& a)
+    static __device__ __forceinline__ void phase1(const float* soft2, int n, float pm1, float pm2, unsigned pps,
+                                                  float (&v)[K::RP[J + 1] - K::RP[J]])
     {
         constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
         if constexpr (Q < DEG) {
             constexpr int off = K::COL[E0 + Q] * 2 * Z + K::SH[E0 + Q];
             const float sv = soft2[n + off];
-            const float pabs = ppos == (unsigned)Q ? pm2 : pm1;                              // decoders.cpp:5152
-            const float pval = __uint_as_float(__float_as_uint(pabs) ^ ((pps << Q) & 0x80000000u));   // :5156
-            const float vv = sv - pval;                                                      // :5158
-            v[Q] = vv;
-            a.sacc ^= __float_as_uint(vv);
-            const float x = fabsf(vv);
-            a.c2 = fminf(a.c2, fmaxf(a.c1, x));                                              // :5012-5027
-            a.c1 = fminf(a.c1, x);
-            phase1<J, Q + 1>(soft2, n, pm1, pm2, pps, ppos, v, a);
+            const float pabs = (pps & (0x10000u << Q)) ? pm2 : pm1;                          // :5152
+            const float pval = __uint_as_float(__float_as_uint(pabs) ^ ((pps << (31 - Q)) & 0x80000000u));   // :5156
+            v[Q] = sv - pval;                                                                // :5158
+            phase1<J, Q + 1>(soft2, n, pm1, pm2, pps, v);
         }
     }
 
+    // minima and sign parity of the row from the v2c values, two edges per step
     template <int J, int Q>
-    static __device__ __forceinline__ void phase2(float* soft2, int n, const float (&v)[K::RP[J + 1] - K::RP[J]], float c1,
-                                                  unsigned m1x, unsigned m2x, unsigned& S, unsigned& pos)
+    static __device__ __forceinline__ void reduce(const float (&v)[K::RP[J + 1] - K::RP[J]], RowAcc& a, unsigned& sacc)
+    {
+        constexpr int DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q + 1 < DEG) {
+            sacc = sacc ^ __float_as_uint(v[Q]) ^ __float_as_uint(v[Q + 1]);
+            track2(a, fabsf(v[Q]), fabsf(v[Q + 1]));
+            reduce<J, Q + 2>(v, a, sacc);
+        } else if constexpr (Q < DEG) {
+            sacc ^= __float_as_uint(v[Q]);
+            track1(a, fabsf(v[Q]));
+        }
+    }
+
+    // store nv at soft2[n + OFF] and at its mirror in the doubled column: lanes that wrapped (n >= THR) mirror
+    // downwards, the others upwards -- two predicated stores with immediate offsets, no address arithmetic
+    template <int OFF, int THR>
+    static __device__ __forceinline__ void store2(unsigned saddr, int n, float nv)
+    {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "st.shared.f32 [%0+%2], %5;\n\t"
+                     "setp.ge.s32 p, %1, %6;\n\t"
+                     "@p st.shared.f32 [%0+%3], %5;\n\t"
+                     "@!p st.shared.f32 [%0+%4], %5;\n\t}"
+                     :: "r"(saddr), "r"(n), "n"(4 * OFF), "n"(4 * (OFF - Z)), "n"(4 * (OFF + Z)), "f"(nv), "n"(THR) : "memory");
+    }
+    template <int OFF>
+    static __device__ __forceinline__ void store2_noshift(unsigned saddr, float nv)
+    {
+        asm volatile("st.shared.f32 [%0+%1], %3;\n\tst.shared.f32 [%0+%2], %3;"
+                     :: "r"(saddr), "n"(4 * OFF), "n"(4 * (OFF + Z)), "f"(nv) : "memory");
+    }
+
+    template <int J, int Q>
+    static __device__ __forceinline__ void phase2(unsigned saddr, int n, const float (&v)[K::RP[J + 1] - K::RP[J]], float c1,
+                                                  unsigned m1x, unsigned m2x, unsigned& S, unsigned& MF)
     {
         constexpr int E0 = K::RP[J];
         if constexpr (Q >= 0) {
             constexpr int sh = K::SH[E0 + Q];
             constexpr int off = K::COL[E0 + Q] * 2 * Z + sh;
             const bool ismin = fabsf(v[Q]) == c1;
-            pos = ismin ? (unsigned)Q : pos;                                                 // reverse scan: the first minimum wins
+            if (ismin) MF |= 0x10000u << Q;
             const unsigned cv = (ismin ? m2x : m1x) ^ (__float_as_uint(v[Q]) & 0x80000000u); // :5193-5198
-            S = (S >> 1) | (cv & 0x80000000u);
+            S = __funnelshift_l(cv, S, 1);                                                   // S = S << 1 | sign(cv)
             const float nv = v[Q] + __uint_as_float(cv);                                     // :5199-5204
-            soft2[n + off] = nv;
-            if constexpr (sh == 0) soft2[n + off + Z] = nv;                                  // a zero shift never wraps
-            else {
-                if (n >= Z - sh) soft2[n + off - Z] = nv;
-                else soft2[n + off + Z] = nv;
-            }
-            phase2<J, Q - 1>(soft2, n, v, c1, m1x, m2x, S, pos);
+            if constexpr (sh == 0) store2_noshift<off>(saddr, nv);                           // a zero shift never wraps
+            else store2<off, Z - sh>(saddr, n, nv);
+            phase2<J, Q - 1>(saddr, n, v, c1, m1x, m2x, S, MF);
         }
     }
 
     template <int J>
-    static __device__ __forceinline__ void layer(float* soft2, int n, float& m1, float& m2, unsigned& ps)
+    static __device__ __forceinline__ void layer(float* soft2, unsigned saddr, int n, float& m1, float& m2, unsigned& ps)
     {
         constexpr int DEG = K::RP[J + 1] - K::RP[J];
         float v[DEG];
+        phase1<J, 0>(soft2, n, m1, m2, ps, v);
         RowAcc a;
-        a.c1 = __int_as_float(0x7f800000); a.c2 = a.c1; a.sacc = 0;
-        phase1<J, 0>(soft2, n, m1, m2, ps, ps & 0xffu, v, a);
+        a.c1 = __int_as_float(0x7f800000); a.c2 = a.c1;
+        unsigned sacc = 0;
+        reduce<J, 0>(v, a, sacc);
         const float n1 = fminf(fmaxf(a.c1 - 0.4f, 0.0f), 32767.0f);                          // :5166-5168, :5131-5137
         const float n2 = fminf(fmaxf(a.c2 - 0.4f, 0.0f), 32767.0f);
-        const unsigned rs = a.sacc & 0x80000000u;
-        unsigned S = 0, pos = 0;
-        phase2<J, DEG - 1>(soft2, n, v, a.c1, __float_as_uint(n1) ^ rs, __float_as_uint(n2) ^ rs, S, pos);
-        m1 = n1; m2 = n2; ps = S | pos;                                                      // :5179
+        const unsigned rs = sacc & 0x80000000u;
+        unsigned S = 0, MF = 0;
+        phase2<J, DEG - 1>(saddr, n, v, a.c1, __float_as_uint(n1) ^ rs, __float_as_uint(n2) ^ rs, S, MF);
+        m1 = n1; m2 = n2; ps = S | MF;                                                       // :5179
     }
 
     template <int J>
-    static __device__ __forceinline__ void layers(float* soft2, int n, bool active, float (&m1)[B], float (&m2)[B], unsigned (&ps)[B])
+    static __device__ __forceinline__ void layers(float* soft2, unsigned saddr, int n, bool active, float (&m1)[B], float (&m2)[B], unsigned (&ps)[B])
     {
         if constexpr (J < B) {
-            if (ALL_ACTIVE || active) layer<J>(soft2, n, m1[J], m2[J], ps[J]);
+            if (ALL_ACTIVE || active) layer<J>(soft2, saddr, n, m1[J], m2[J], ps[J]);
             __syncthreads();
-            layers<J + 1>(soft2, n, active, m1, m2, ps);
+            layers<J + 1>(soft2, saddr, n, active, m1, m2, ps);
         }
     }
 
@@ -142,6 +185,7 @@ struct LmsSpec {
         const int tid = threadIdx.x;
         const bool active = tid < Z;
         const bool noexit = io.flags & 8u;                       // LDPCB200_NO_EARLY_EXIT
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(soft2 + tid);     // shared-window byte address of this lane
         float m1[B], m2[B];
         unsigned ps[B];
 
@@ -187,7 +231,7 @@ struct LmsSpec {
             if (!parity) { ret = 1; locked = 1; }
             for (iter = 0; iter < io.maxiter; iter++) {
                 if (!parity && !noexit) break;                                          // :5119
-                layers<0>(soft2, tid, active, m1, m2, ps);
+                layers<0>(soft2, saddr, tid, active, m1, m2, ps);
                 parity = syndrome(soft2, hb, tid);                                      // :5281-5284
                 if (!parity && !locked) { ret = iter + 1; locked = 1; }
                 if (!parity && !noexit) break;
