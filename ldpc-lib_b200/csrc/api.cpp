@@ -2,6 +2,7 @@
 // dispatch to the CUDA kernels.  No decoding arithmetic lives here and nothing here falls back to a
 // CPU path: without a usable CUDA device every compute entry point fails with LDPCB200_ENODEV.
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -14,10 +15,10 @@
 namespace ldpcb200 {
 size_t minsum_workspace_bytes(int decoder_id, int precision, const QcHost& g, int nt);
 cudaError_t launch_minsum_generic(int decoder_id, int precision, const QcDev& g, const DecParams& dp,
-                                  const FrameIO& io, char* ws, size_t ws_stride, int grid, int nt, cudaStream_t s);
+                                  const FrameIO& io, char* ws, size_t ws_stride, size_t smem_ws, int grid, int nt, cudaStream_t s);
 size_t sumprod_workspace_bytes(int decoder_id, const QcHost& g, int nt);
 cudaError_t launch_sumprod_generic(int decoder_id, const QcDev& g, const DecParams& dp, const FrameIO& io,
-                                   char* ws, size_t ws_stride, int grid, int nt, cudaStream_t s);
+                                   char* ws, size_t ws_stride, size_t smem_ws, int grid, int nt, cudaStream_t s);
 }
 
 namespace ldpcb200 {
@@ -94,7 +95,7 @@ struct ldpcb200_handle_s {
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf tables, ws, counters, next, bpsynd, coef;
-    size_t ws_stride = 0;
+    size_t ws_stride = 0, smem_ws = 0;      // smem_ws != 0: the table-driven kernel keeps its state in shared memory
     int grid = 0, nt = 0;
     Slot slot[2];
     FastPlan fast{};
@@ -159,9 +160,9 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
         CU(launch_ims_fast(h->fast, h->gd, h->dp, io, (double*)h->coef.p, std::max(fgrid, 1), h->stream));
         h->last_launches++;
     } else if (is_minsum(h->decoder_id)) {
-        CU(launch_minsum_generic(h->decoder_id, h->p.precision, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, grid, h->nt, h->stream));
+        CU(launch_minsum_generic(h->decoder_id, h->p.precision, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, h->smem_ws, grid, h->nt, h->stream));
     } else {
-        CU(launch_sumprod_generic(h->decoder_id, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, grid, h->nt, h->stream));
+        CU(launch_sumprod_generic(h->decoder_id, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, h->smem_ws, grid, h->nt, h->stream));
     }
     h->last_launches++;
     return 0;
@@ -284,7 +285,17 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
         size_t wsb = is_minsum(decoder_id) ? minsum_workspace_bytes(decoder_id, p.precision, h->g, h->nt)
                                            : sumprod_workspace_bytes(decoder_id, h->g, h->nt);
         h->ws_stride = (wsb + 255) & ~(size_t)255;
-        CU(h->ws.reserve(h->ws_stride * h->grid));
+        // Measured on B200 (profiles/r01_all_decoders_v1 vs _v2): staging the table-driven kernels' state in shared
+        // memory does not pay -- they are bound by fp64 / exp / log throughput and occupancy, and the L2-resident
+        // workspace allows more CTAs per SM -- so it is opt-in (LDPCB200_WS_SMEM=1).
+        const char* sm = getenv("LDPCB200_WS_SMEM");
+        if (h->ws_stride + 8192 <= (size_t)h->smem_per_block && sm && *sm == '1') {   // 8 KB: the kernels' static shared variables
+            h->smem_ws = h->ws_stride;
+            int per_sm = (int)((size_t)h->smem_per_sm / (h->smem_ws + 8192 + 1024));
+            per_sm = std::min(per_sm, h->nt == 256 ? 2 : 1);
+            h->grid = h->num_sms * std::max(per_sm, 1);
+        }
+        CU(h->ws.reserve(h->smem_ws ? 256 : h->ws_stride * h->grid));
         CU(h->counters.reserve(8 * sizeof(unsigned long long)));
         CU(h->next.reserve(256));
         CU(h->bpsynd.reserve((size_t)h->g.R + 16));
@@ -340,7 +351,7 @@ int ldpcb200_kernel_info(ldpcb200_handle h, int* fast, int* threads, int* frames
     if (threads) *threads = h->fast.ok ? h->fast.threads : h->nt;
     if (frames_per_cta) *frames_per_cta = h->fast.ok ? h->fast.frames_per_cta : 1;
     if (ctas_per_sm) *ctas_per_sm = h->fast.ok ? h->fast.ctas_per_sm : h->grid / std::max(h->num_sms, 1);
-    if (smem_bytes) *smem_bytes = h->fast.ok ? (int)h->fast.smem_bytes : 0;
+    if (smem_bytes) *smem_bytes = h->fast.ok ? (int)h->fast.smem_bytes : (int)h->smem_ws;
     return 0;
 }
 

@@ -298,12 +298,23 @@ struct ImsGeneric {
 template <class Dec>
 __global__ void __launch_bounds__(512) generic_minsum_kernel(QcDev g, DecParams dp, FrameIO io, char* ws, size_t ws_stride)
 {
-    char* w = ws + (size_t)blockIdx.x * ws_stride;
+    // the decoder state lives in shared memory when it fits (ws == nullptr), else in this CTA's slice of an
+    // L2-resident global workspace
+    extern __shared__ __align__(16) char dyn_ws[];
+    char* w = ws ? ws + (size_t)blockIdx.x * ws_stride : dyn_ws;
     for (;;) {
         int f = next_frame(io);
         if (f >= io.nf) break;
         Dec::frame(g, dp, io, f, w);
     }
+}
+
+template <class Kern>
+static void launch_one(Kern kern, const QcDev& g, const DecParams& dp, const FrameIO& io, char* ws, size_t ws_stride, size_t smem_ws,
+                       int grid, int nt, cudaStream_t s)
+{
+    if (smem_ws) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+    kern<<<grid, nt, smem_ws, s>>>(g, dp, io, smem_ws ? nullptr : ws, ws_stride);
 }
 
 size_t minsum_workspace_bytes(int decoder_id, int precision, const QcHost& g, int nt)
@@ -317,19 +328,19 @@ size_t minsum_workspace_bytes(int decoder_id, int precision, const QcHost& g, in
 }
 
 cudaError_t launch_minsum_generic(int decoder_id, int precision, const QcDev& g, const DecParams& dp,
-                                  const FrameIO& io, char* ws, size_t ws_stride, int grid, int nt, cudaStream_t s)
+                                  const FrameIO& io, char* ws, size_t ws_stride, size_t smem_ws, int grid, int nt, cudaStream_t s)
 {
     switch (decoder_id) {
     case LDPCB200_LMS_DEC:
-        if (precision == 32) generic_minsum_kernel<LmsGeneric<float>><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride);
-        else generic_minsum_kernel<LmsGeneric<double>><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride);
+        if (precision == 32) launch_one(generic_minsum_kernel<LmsGeneric<float>>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s);
+        else launch_one(generic_minsum_kernel<LmsGeneric<double>>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s);
         break;
     case LDPCB200_MS_DEC:
-        if (precision == 32) generic_minsum_kernel<MsGeneric<float>><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride);
-        else generic_minsum_kernel<MsGeneric<double>><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride);
+        if (precision == 32) launch_one(generic_minsum_kernel<MsGeneric<float>>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s);
+        else launch_one(generic_minsum_kernel<MsGeneric<double>>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s);
         break;
     case LDPCB200_IMS_DEC:
-        generic_minsum_kernel<ImsGeneric><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride);
+        launch_one(generic_minsum_kernel<ImsGeneric>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s);
         break;
     default: return cudaErrorInvalidValue;
     }

@@ -614,12 +614,23 @@ struct IaspGeneric {
 template <class Dec>
 __global__ void __launch_bounds__(512) generic_sumprod_kernel(QcDev g, DecParams dp, FrameIO io, char* ws, size_t ws_stride)
 {
-    char* w = ws + (size_t)blockIdx.x * ws_stride;
+    // the decoder state lives in shared memory when it fits (ws == nullptr), else in this CTA's slice of an
+    // L2-resident global workspace
+    extern __shared__ __align__(16) char dyn_ws[];
+    char* w = ws ? ws + (size_t)blockIdx.x * ws_stride : dyn_ws;
     for (;;) {
         int f = next_frame(io);
         if (f >= io.nf) break;
         Dec::frame(g, dp, io, f, w);
     }
+}
+
+template <class Kern>
+static void launch_one(Kern kern, const QcDev& g, const DecParams& dp, const FrameIO& io, char* ws, size_t ws_stride, size_t smem_ws,
+                       int grid, int nt, cudaStream_t s)
+{
+    if (smem_ws) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+    kern<<<grid, nt, smem_ws, s>>>(g, dp, io, smem_ws ? nullptr : ws, ws_stride);
 }
 
 size_t sumprod_workspace_bytes(int decoder_id, const QcHost& g, int nt)
@@ -636,15 +647,15 @@ size_t sumprod_workspace_bytes(int decoder_id, const QcHost& g, int nt)
 }
 
 cudaError_t launch_sumprod_generic(int decoder_id, const QcDev& g, const DecParams& dp, const FrameIO& io,
-                                   char* ws, size_t ws_stride, int grid, int nt, cudaStream_t s)
+                                   char* ws, size_t ws_stride, size_t smem_ws, int grid, int nt, cudaStream_t s)
 {
     switch (decoder_id) {
-    case LDPCB200_TASP_DEC: generic_sumprod_kernel<TaspGeneric><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride); break;
-    case LDPCB200_ASP_DEC:  generic_sumprod_kernel<AspGeneric><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride); break;
-    case LDPCB200_BP_DEC:   generic_sumprod_kernel<BpGeneric><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride); break;
-    case LDPCB200_SP_DEC:   generic_sumprod_kernel<SpGeneric><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride); break;
-    case LDPCB200_LCHE_DEC: generic_sumprod_kernel<LcheGeneric><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride); break;
-    case LDPCB200_IASP_DEC: generic_sumprod_kernel<IaspGeneric><<<grid, nt, 0, s>>>(g, dp, io, ws, ws_stride); break;
+    case LDPCB200_TASP_DEC: launch_one(generic_sumprod_kernel<TaspGeneric>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s); break;
+    case LDPCB200_ASP_DEC:  launch_one(generic_sumprod_kernel<AspGeneric>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s); break;
+    case LDPCB200_BP_DEC:   launch_one(generic_sumprod_kernel<BpGeneric>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s); break;
+    case LDPCB200_SP_DEC:   launch_one(generic_sumprod_kernel<SpGeneric>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s); break;
+    case LDPCB200_LCHE_DEC: launch_one(generic_sumprod_kernel<LcheGeneric>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s); break;
+    case LDPCB200_IASP_DEC: launch_one(generic_sumprod_kernel<IaspGeneric>, g, dp, io, ws, ws_stride, smem_ws, grid, nt, s); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -144,7 +144,7 @@ class Decoder:
         v = [C.c_int() for _ in range(5)]
         _check(lib().ldpcb200_kernel_info(self._h, *[C.byref(x) for x in v]))
         d = dict(zip(("fast", "threads", "frames_per_cta", "ctas_per_sm", "smem_bytes"), [x.value for x in v]))
-        d["name"] = {0: "generic (table-driven, L2 workspace)", 1: "lms_fast_kernel (table-driven, shared memory)",
+        d["name"] = {0: "generic (table-driven, state in %s)" % ("shared memory" if d["smem_bytes"] else "an L2-resident workspace"), 1: "lms_fast_kernel (table-driven, shared memory)",
                      2: "lms_spec (code-specialised, ahead of time)", 3: "lms_spec_jit (code-specialised, NVRTC)"}.get(d["fast"], "?")
         return d
 
