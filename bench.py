@@ -41,6 +41,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CODE, Z, SNR_DB, MAXITER, DECODER = "ref32x16_b", 256, 2.0, 10, 8      # 8 = LMS_DEC
 FRAMES_PER_GPU = 1 << 20
 METRIC, UNIT = "decoded_info_gbps_10iter", "Gbit/s"
+TRAFFIC_BYTES_PER_FRAME = (2148847000 + 19339264) / 65536        # ncu capture of the bench kernel: 33 084 B per frame
 
 
 def load_binding():
@@ -243,6 +244,20 @@ def run_ours(args):
     t3 = time.perf_counter()
     e2e_ms = 1e3 * (t3 - t2)
 
+    # the decode entry point with HOST buffers: pinned fp32 LLRs in, packed decisions + iteration counts out, all
+    # copies inside the timed region (PCIe-bound: 32 KiB of LLR per 4096 information bits)
+    hn = min(frames, 1 << 15)
+    h_llr = torch.empty((hn, N), dtype=torch.float32).pin_memory()
+    h_llr.copy_(llr[:hn])
+    h_np = h_llr.numpy()
+    dec.decode(h_np[:1024], MAXITER, packed=True, no_early_exit=True)
+    barrier()
+    t4 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.decode(h_np, MAXITER, packed=True, no_early_exit=True)
+    barrier()
+    host_ms = 1e3 * (time.perf_counter() - t4)
+
     def maxred(x):
         if world == 1:
             return x
@@ -250,7 +265,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    dev_ms, wall_ms, e2e_ms, ee_ms = maxred(dev_ms), maxred(wall_ms), maxred(e2e_ms), maxred(ee_ms)
+    dev_ms, wall_ms, e2e_ms, ee_ms, host_ms = maxred(dev_ms), maxred(wall_ms), maxred(e2e_ms), maxred(ee_ms), maxred(host_ms)
 
     if rank == 0:
         total_frames = frames * world * args.steps
@@ -273,10 +288,15 @@ def run_ours(args):
                 "e2e": {"value": total_frames * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 72,
                         "d2h_bytes_per_step": 48 + 4 * frames, "gpu_launches": e2e_launches,
                         "call": "ldpcb200_simulate (host sim-params -> host counters + per-frame records)"},
+                "e2e_host_llr": {"value": hn * world * args.steps * K / (host_ms * 1e-3) / 1e9, "unit": UNIT, "frames_per_step": hn,
+                                 "h2d_bytes_per_step": hn * N * 4, "d2h_bytes_per_step": hn * (dec.nwords * 4 + 4),
+                                 "call": "ldpcb200_decode_batch (pinned host fp32 LLRs -> host packed decisions + iteration counts)"},
                 "early_exit": {"value": frames * world * K / (ee_ms * 1e-3) / 1e9, "unit": UNIT, "avg_iterations": avg_iters,
                                "frame_failure_rate": fer_proxy},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame},
+                             "traffic": TRAFFIC_BYTES_PER_FRAME * frames, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame,
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_spec_v1 (ncu --set full, "
+                                               "65536 frames) scaled to this launch"},
                 # the binding roofline: min-sum is compare / select / logic work that issues on the
                 # ALU pipe (64 lanes / clk / SM); 13.9 ALU-pipe and 25.6 total SASS instructions per edge update
                 # (profiles/r01_lms_spec_v1_*: ncu source page and cuobjdump counts of the specialised kernel)

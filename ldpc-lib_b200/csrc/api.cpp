@@ -22,8 +22,8 @@ cudaError_t launch_sumprod_generic(int decoder_id, const QcDev& g, const DecPara
 }
 
 namespace ldpcb200 {
-bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem);
-std::string lms_spec_generate(const QcHost& g, int zp, int minb);
+bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant);
+std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant);
 bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<char>& cubin, std::string& why);
 }
 
@@ -586,12 +586,12 @@ int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int
 {
     QcHost g;
     if (!g.build(hd, b, c, Z)) return fail(LDPCB200_EINVAL, "bad base matrix");
-    int zp, minb;
+    int zp, minb, variant;
     size_t smem;
-    if (!lms_spec_geometry(g, 233472, 232448, &zp, &minb, &smem)) return fail(LDPCB200_EUNSUPPORTED, "code does not suit the register-state kernel");
+    if (!lms_spec_geometry(g, 233472, 232448, &zp, &minb, &smem, &variant)) return fail(LDPCB200_EUNSUPPORTED, "code does not suit the code-specialised kernel");
     std::vector<char> cubin;
     std::string why;
-    if (!lms_spec_compile(lms_spec_generate(g, zp, minb), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());
+    if (!lms_spec_compile(lms_spec_generate(g, zp, minb, variant), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());
     if (cubin_bytes) *cubin_bytes = (int)cubin.size();
     return 0;
 }

@@ -137,6 +137,19 @@ static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, un
     return (float)(-o[bit]);
 }
 
+// All m/2 LLRs carried by one PAM component (cidx = 2 * symbol + component) of a QAM-16/64/256 frame: one noise
+// sample, one pass through pam_demod.  out[b] is the LLR of bit (cidx / 2) * m + (cidx & 1) * m/2 + b; the
+// caller applies the puncturing.  Bit-identical to channel_llr_qam() bit by bit.
+static __device__ __noinline__ void channel_llr_qam_component(const ChannelParams& ch, unsigned long long frame, int cidx, float out[4])
+{
+    const int half = ch.m >> 1;
+    float nz = channel_noise(ch, frame, (unsigned int)cidx);
+    double x = (double)nz * ch.sigma_d - (double)((1 << half) - 1);
+    double o[4];
+    pam_demod(x, 2.0 * ch.sigma_d * ch.sigma_d, ch.T, ch.m, 0, o);
+    for (int b = 0; b < 4; b++) out[b] = b < half ? (float)(-o[b]) : 0.0f;
+}
+
 // Channel LLR (log P0/P1, the decoder-side sign) of bit i of frame f for the all-zero codeword.
 __device__ __forceinline__ float channel_llr(const ChannelParams& ch, unsigned long long frame, int i)
 {

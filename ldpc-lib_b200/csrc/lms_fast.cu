@@ -166,10 +166,25 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
         // ---- first load: channel LLRs -> both copies of every block column; check state := 0 (:5088-5108)
         if (io.ch.enabled) {
             const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
-            for (int i = tid; i < N; i += nt) {
-                const int col = i / Z, k = i - col * Z;
-                const float x = channel_llr(io.ch, frame, i);
-                soft2[col * 2 * Z + k] = x; soft2[col * 2 * Z + Z + k] = x;
+            if (io.ch.m > 2) {
+                // QAM-16/64/256: one thread per PAM component, m/2 LLRs from one demodulation
+                const int half = io.ch.m >> 1, ncomp = 2 * (N / io.ch.m);
+                for (int c = tid; c < ncomp; c += nt) {
+                    float o[4];
+                    channel_llr_qam_component(io.ch, frame, c, o);
+                    const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
+                    for (int b = 0; b < half; b++) {
+                        const int i = i0 + b, col = i / Z, k = i - col * Z;
+                        const float x = i >= io.ch.punct_start ? io.ch.punct_value : o[b];
+                        soft2[col * 2 * Z + k] = x; soft2[col * 2 * Z + Z + k] = x;
+                    }
+                }
+            } else {
+                for (int i = tid; i < N; i += nt) {
+                    const int col = i / Z, k = i - col * Z;
+                    const float x = channel_llr(io.ch, frame, i);
+                    soft2[col * 2 * Z + k] = x; soft2[col * 2 * Z + Z + k] = x;
+                }
             }
         } else if (io.llr_dtype == LDPCB200_F32) {
             const float* y = (const float*)io.llr + (size_t)f * N;
@@ -271,24 +286,33 @@ int find_lms_spec_aot(const QcHost& g);
 void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size_t* smem);
 cudaError_t launch_lms_spec_aot(int idx, const FrameIO& io, int grid, cudaStream_t s);
 
-const void* lms_spec_jit(const QcHost& g, int zp, int minb, std::string& why);
+const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, std::string& why);
 cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const FrameIO& io, int grid, cudaStream_t s);
 
-// launch geometry of the code-specialised kernel for g; false if the code does not suit it
-bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem)
+// launch geometry of the code-specialised kernel for g; false if the code does not suit it.
+// *variant = 0: every block column doubled in shared memory, all check state in registers (small codes);
+//            1: single copy + sign/position words in shared memory, min1/min2 in registers (large codes)
+bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant)
 {
-    if (g.b > 32 || g.E > 512 || g.Z > 1024 || g.maxdeg > 16) return false;     // row word: 16 sign bits + 16 minimum flags
+    if (g.E > 512 || g.Z > 1024 || g.maxdeg > MAXDEG_FAST) return false;
     *zp = (g.Z + 31) & ~31;
     const int hw = *zp / 32;
-    *smem = sizeof(float) * (2 * (size_t)g.N + (g.c * hw > 4 ? g.c * hw : 4));
-    if (*smem > (size_t)smem_per_block) return false;
-    const int regs = 3 * g.b + 44;                           // check state of every block row + working set
-    int m = (int)((size_t)smem_per_sm / (*smem + 1024));
-    m = std::min(m, 2048 / *zp);
-    m = std::min(m, 65536 / (*zp * regs));
-    if (m < 1) return false;
-    *minb = std::min(m, 16);
-    return true;
+    const size_t hb = (size_t)(g.c * hw > 4 ? g.c * hw : 4);
+    for (int v = 0; v < 2; v++) {
+        const size_t words = v == 0 ? 2 * (size_t)g.N + hb : (size_t)g.N + (size_t)g.R + hb;
+        const int regs = (v == 0 ? 3 : 2) * g.b + 48;              // check state of every block row + working set
+        if (v == 0 && (g.b > 32 || g.maxdeg > 16)) continue;
+        if (sizeof(float) * words > (size_t)smem_per_block) continue;
+        int m = (int)((size_t)smem_per_sm / (sizeof(float) * words + 1024));
+        m = std::min(m, 2048 / *zp);
+        m = std::min(m, 65536 / (*zp * regs));
+        if (m < 1) continue;
+        *smem = sizeof(float) * words;
+        *minb = std::min(m, 16);
+        *variant = v;
+        return true;
+    }
+    return false;
 }
 
 FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block, int allow_jit)
@@ -306,11 +330,11 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
         }
     }
     if (allow_jit && !(no_spec && *no_spec == '1')) {       // compile one for this matrix
-        int zp, minb;
+        int zp, minb, variant;
         size_t smem;
-        if (lms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem)) {
+        if (lms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem, &variant)) {
             std::string why;
-            const void* k = lms_spec_jit(g, zp, minb, why);
+            const void* k = lms_spec_jit(g, zp, minb, variant, why);
             if (k) {
                 p.ok = 1; p.variant = 2; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem;
                 p.jit_kernel = k;
@@ -318,7 +342,7 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
             }
             p.note = why;
         } else
-            p.note = "code does not suit the register-state kernel (b > 32, too many edges, or shared memory)";
+            p.note = "code does not suit the code-specialised kernel (too many edges / block rows for registers and shared memory)";
     }
     if (g.E > MAXE || g.b > MAXB || g.maxdeg > MAXDEG_FAST || g.Z > 512) return p;
     const size_t smem = lms_fast_smem(g);

@@ -2,7 +2,8 @@
 // base matrix baked in at compile time.  It is compiled once per code -- ahead of time for the frozen benchmark
 // matrices (lms_spec_aot.cu), at run time through NVRTC for any other code (spec_jit.cpp) -- from a generated
 //
-//   struct Code { static constexpr int B, C, Z, E, ZP, MINB;                 // ZP = threads, MINB = CTAs per SM
+//   struct Code { static constexpr int B, C, Z, E, ZP, MINB, MAXDEG;         // ZP = threads, MINB = CTAs per SM
+//                 static constexpr bool DOUBLED, PS_SMEM;                    // layout variant, see below
 //                 static constexpr int RP[B + 1], COL[E], SH[E];             // compile-time copies
 //                 static const int* rt_rp() / rt_col() / rt_sh(); };         // __constant__ copies for run-time indexing
 //
@@ -11,7 +12,10 @@
 // is two predicated stores with immediate offsets), (2) the check-row state (min1, min2, signs|pos) of all B
 // block rows of a lane lives in REGISTERS across iterations -- shared memory holds only the doubled posteriors,
 // 8N bytes per frame (64 KB at N = 8192 -> 3 frames per SM instead of 2), and (3) the position compare is
-// against an immediate.  This header must stay free of #include (NVRTC compiles it as one string together with
+// against an immediate.  Large codes (the 46 x 68, Z = 384 "BG1-shaped" one: 104 KB of posteriors, 46 block
+// rows) use the second layout variant: DOUBLED = false (every block column stored once; the wrapped lanes
+// read / write through a predicated second instruction with its own immediate) and PS_SMEM = true (the sign /
+// position word of each check row in shared memory, only min1 / min2 in registers).  This header must stay free of #include (NVRTC compiles it as one string together with
 // frame_io.h and channel.cuh).
 #pragma once
 
@@ -24,7 +28,11 @@ struct LmsSpec {
     static constexpr int NB = (Z + 31) / 32;
     static constexpr int NWORDS = (N + 31) / 32;
     static constexpr bool ALL_ACTIVE = (Z == ZP);
-    static constexpr int SMEM_WORDS = 2 * N + (C * HW > 4 ? C * HW : 4);
+    static constexpr bool DOUBLED = K::DOUBLED, PS_SMEM = K::PS_SMEM;
+    static constexpr bool USE_POS = K::MAXDEG > 16;          // row word: 16 signs + 16 minimum flags, or 24 signs + position
+    static constexpr int CS = DOUBLED ? 2 * Z : Z;           // stride of a block column in shared memory
+    static constexpr int SOFT_WORDS = C * CS;
+    static constexpr int PS_WORDS = PS_SMEM ? R : 0;
 
     // ---- one block row J of one lane.  The edge loops are compile-time recursions so that every per-edge
     // constant (K::COL, K::SH) is used in a constant expression: the tables never exist in device memory.
@@ -47,17 +55,23 @@ struct LmsSpec {
     }
 
     template <int J, int Q>
-    static __device__ __forceinline__ void phase1(const float* soft2, int n, float pm1, float pm2, unsigned pps,
+    static __device__ __forceinline__ void phase1(const float* soft2, unsigned saddr, int n, float pm1, float pm2, unsigned pps,
                                                   float (&v)[K::RP[J + 1] - K::RP[J]])
     {
         constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
         if constexpr (Q < DEG) {
-            constexpr int off = K::COL[E0 + Q] * 2 * Z + K::SH[E0 + Q];
-            const float sv = soft2[n + off];
-            const float pabs = (pps & (0x10000u << Q)) ? pm2 : pm1;                          // :5152
+            constexpr int sh = K::SH[E0 + Q];
+            constexpr int off = K::COL[E0 + Q] * CS + sh;
+            float sv;
+            if constexpr (DOUBLED || sh == 0) sv = soft2[n + off];
+            else sv = load_wrapped<off, Z - sh>(saddr, n);
+            bool flag;
+            if constexpr (USE_POS) flag = (pps >> 24) == (unsigned)Q;
+            else flag = pps & (0x10000u << Q);
+            const float pabs = flag ? pm2 : pm1;                                             // :5152
             const float pval = __uint_as_float(__float_as_uint(pabs) ^ ((pps << (31 - Q)) & 0x80000000u));   // :5156
             v[Q] = sv - pval;                                                                // :5158
-            phase1<J, Q + 1>(soft2, n, pm1, pm2, pps, v);
+            phase1<J, Q + 1>(soft2, saddr, n, pm1, pm2, pps, v);
         }
     }
 
@@ -74,6 +88,33 @@ struct LmsSpec {
             sacc ^= __float_as_uint(v[Q]);
             track1(a, fabsf(v[Q]));
         }
+    }
+
+    // single-copy layout: lane n reads / writes bit (n + shift) mod Z of the column; lanes n >= THR have wrapped
+    template <int OFF, int THR>
+    static __device__ __forceinline__ float load_wrapped(unsigned saddr, int n)
+    {
+        float x;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "setp.ge.s32 p, %2, %5;\n\t"
+                     "@p ld.shared.f32 %0, [%1+%4];\n\t"
+                     "@!p ld.shared.f32 %0, [%1+%3];\n\t}"
+                     : "=f"(x) : "r"(saddr), "r"(n), "n"(4 * OFF), "n"(4 * (OFF - Z)), "n"(THR) : "memory");
+        return x;
+    }
+    template <int OFF, int THR>
+    static __device__ __forceinline__ void store_wrapped(unsigned saddr, int n, float nv)
+    {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "setp.ge.s32 p, %1, %5;\n\t"
+                     "@p st.shared.f32 [%0+%3], %4;\n\t"
+                     "@!p st.shared.f32 [%0+%2], %4;\n\t}"
+                     :: "r"(saddr), "r"(n), "n"(4 * OFF), "n"(4 * (OFF - Z)), "f"(nv), "n"(THR) : "memory");
+    }
+    template <int OFF>
+    static __device__ __forceinline__ void store_plain(unsigned saddr, float nv)
+    {
+        asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(saddr), "n"(4 * OFF), "f"(nv) : "memory");
     }
 
     // store nv at soft2[n + OFF] and at its mirror in the doubled column: lanes that wrapped (n >= THR) mirror
@@ -102,14 +143,20 @@ struct LmsSpec {
         constexpr int E0 = K::RP[J];
         if constexpr (Q >= 0) {
             constexpr int sh = K::SH[E0 + Q];
-            constexpr int off = K::COL[E0 + Q] * 2 * Z + sh;
+            constexpr int off = K::COL[E0 + Q] * CS + sh;
             const bool ismin = fabsf(v[Q]) == c1;
-            if (ismin) MF |= 0x10000u << Q;
+            if constexpr (USE_POS) MF = ismin ? ((unsigned)Q << 24) : MF;                    // reverse scan: the first minimum wins
+            else { if (ismin) MF |= 0x10000u << Q; }
             const unsigned cv = (ismin ? m2x : m1x) ^ (__float_as_uint(v[Q]) & 0x80000000u); // :5193-5198
             S = __funnelshift_l(cv, S, 1);                                                   // S = S << 1 | sign(cv)
             const float nv = v[Q] + __uint_as_float(cv);                                     // :5199-5204
-            if constexpr (sh == 0) store2_noshift<off>(saddr, nv);                           // a zero shift never wraps
-            else store2<off, Z - sh>(saddr, n, nv);
+            if constexpr (DOUBLED) {
+                if constexpr (sh == 0) store2_noshift<off>(saddr, nv);                       // a zero shift never wraps
+                else store2<off, Z - sh>(saddr, n, nv);
+            } else {
+                if constexpr (sh == 0) store_plain<off>(saddr, nv);
+                else store_wrapped<off, Z - sh>(saddr, n, nv);
+            }
             phase2<J, Q - 1>(saddr, n, v, c1, m1x, m2x, S, MF);
         }
     }
@@ -119,7 +166,7 @@ struct LmsSpec {
     {
         constexpr int DEG = K::RP[J + 1] - K::RP[J];
         float v[DEG];
-        phase1<J, 0>(soft2, n, m1, m2, ps, v);
+        phase1<J, 0>(soft2, saddr, n, m1, m2, ps, v);
         RowAcc a;
         a.c1 = __int_as_float(0x7f800000); a.c2 = a.c1;
         unsigned sacc = 0;
@@ -133,10 +180,19 @@ struct LmsSpec {
     }
 
     template <int J>
-    static __device__ __forceinline__ void layers(float* soft2, unsigned saddr, int n, bool active, float (&m1)[B], float (&m2)[B], unsigned (&ps)[B])
+    static __device__ __forceinline__ void layers(float* soft2, unsigned saddr, int n, bool active, float (&m1)[B], float (&m2)[B],
+                                                  unsigned (&ps)[PS_SMEM ? 1 : B])
     {
         if constexpr (J < B) {
-            if (ALL_ACTIVE || active) layer<J>(soft2, saddr, n, m1[J], m2[J], ps[J]);
+            if (ALL_ACTIVE || active) {
+                if constexpr (PS_SMEM) {
+                    unsigned* psw = (unsigned*)(soft2 + SOFT_WORDS) + J * Z + n;
+                    unsigned w = *psw;
+                    layer<J>(soft2, saddr, n, m1[J], m2[J], w);
+                    *psw = w;
+                } else
+                    layer<J>(soft2, saddr, n, m1[J], m2[J], ps[J]);
+            }
             __syncthreads();
             layers<J + 1>(soft2, saddr, n, active, m1, m2, ps);
         }
@@ -148,7 +204,7 @@ struct LmsSpec {
         const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll 4
         for (int col = 0; col < C; col++) {
-            const int bit = (ALL_ACTIVE || tid < Z) ? soft2[col * 2 * Z + tid] < 0.0f : 0;
+            const int bit = (ALL_ACTIVE || tid < Z) ? soft2[col * CS + tid] < 0.0f : 0;
             const unsigned w = __ballot_sync(0xffffffffu, bit);
             if (lane == 0) hb[col * HW + warp] = w;
         }
@@ -180,14 +236,14 @@ struct LmsSpec {
     static __device__ __forceinline__ void kernel(const FrameIO& io)
     {
         extern __shared__ __align__(16) float soft2[];
-        unsigned* hb = (unsigned*)(soft2 + 2 * N);
+        unsigned* hb = (unsigned*)(soft2 + SOFT_WORDS + PS_WORDS);
         int* s_misc = (int*)hb;                                  // aliases hb: only live between frames
         const int tid = threadIdx.x;
         const bool active = tid < Z;
         const bool noexit = io.flags & 8u;                       // LDPCB200_NO_EARLY_EXIT
         const unsigned saddr = (unsigned)__cvta_generic_to_shared(soft2 + tid);     // shared-window byte address of this lane
         float m1[B], m2[B];
-        unsigned ps[B];
+        unsigned ps[PS_SMEM ? 1 : B];
 
         for (;;) {
             __syncthreads();
@@ -198,10 +254,27 @@ struct LmsSpec {
 
             if (io.ch.enabled) {
                 const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
-                for (int i = tid; i < N; i += ZP) {
-                    const int col = i / Z, k = i - col * Z;
-                    const float x = channel_llr(io.ch, frame, i);
-                    soft2[col * 2 * Z + k] = x; soft2[col * 2 * Z + Z + k] = x;
+                if (io.ch.m > 2) {
+                    // QAM-16/64/256: one thread per PAM component, m/2 LLRs from one demodulation
+                    const int half = io.ch.m >> 1, ncomp = 2 * (N / io.ch.m);
+                    for (int c = tid; c < ncomp; c += ZP) {
+                        float o[4];
+                        channel_llr_qam_component(io.ch, frame, c, o);
+                        const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
+                        for (int b = 0; b < half; b++) {
+                            const int i = i0 + b, col = i / Z, k = i - col * Z;
+                            const float x = i >= io.ch.punct_start ? io.ch.punct_value : o[b];
+                            soft2[col * CS + k] = x;
+                            if constexpr (DOUBLED) soft2[col * CS + Z + k] = x;
+                        }
+                    }
+                } else {
+                    for (int i = tid; i < N; i += ZP) {
+                        const int col = i / Z, k = i - col * Z;
+                        const float x = channel_llr(io.ch, frame, i);
+                        soft2[col * CS + k] = x;
+                        if constexpr (DOUBLED) soft2[col * CS + Z + k] = x;
+                    }
                 }
             } else if (io.llr_dtype == 1) {                      // LDPCB200_F32
                 const float* y = (const float*)io.llr + (size_t)f * N;
@@ -209,7 +282,8 @@ struct LmsSpec {
 #pragma unroll 8
                     for (int col = 0; col < C; col++) {
                         const float x = __ldcs(y + col * Z + tid);
-                        soft2[col * 2 * Z + tid] = x; soft2[col * 2 * Z + Z + tid] = x;
+                        soft2[col * CS + tid] = x;
+                        if constexpr (DOUBLED) soft2[col * CS + Z + tid] = x;
                     }
                 }
             } else {
@@ -218,12 +292,20 @@ struct LmsSpec {
 #pragma unroll 8
                     for (int col = 0; col < C; col++) {
                         const float x = (float)__ldcs(y + col * Z + tid);
-                        soft2[col * 2 * Z + tid] = x; soft2[col * 2 * Z + Z + tid] = x;
+                        soft2[col * CS + tid] = x;
+                        if constexpr (DOUBLED) soft2[col * CS + Z + tid] = x;
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < B; j++) { m1[j] = 0.0f; m2[j] = 0.0f; ps[j] = 0u; }     // decoders.cpp:5088-5108
+            for (int j = 0; j < B; j++) { m1[j] = 0.0f; m2[j] = 0.0f; }                 // decoders.cpp:5088-5108
+            if constexpr (PS_SMEM) {
+                unsigned* psw = (unsigned*)(soft2 + SOFT_WORDS);
+                for (int i = tid; i < R; i += ZP) psw[i] = 0u;
+            } else {
+#pragma unroll
+                for (int j = 0; j < B; j++) ps[j] = 0u;
+            }
             __syncthreads();
 
             int parity = syndrome(soft2, hb, tid);                                      // :5111-5115
@@ -242,11 +324,11 @@ struct LmsSpec {
                 if (io.post_dtype == 1) {
                     float* p = (float*)io.post + (size_t)f * N;
                     for (int col = 0; col < C; col++)
-                        if (ALL_ACTIVE || active) p[col * Z + tid] = soft2[col * 2 * Z + tid];
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = soft2[col * CS + tid];
                 } else {
                     double* p = (double*)io.post + (size_t)f * N;
                     for (int col = 0; col < C; col++)
-                        if (ALL_ACTIVE || active) p[col * Z + tid] = (double)soft2[col * 2 * Z + tid];
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = (double)soft2[col * CS + tid];
                 }
             }
             __syncthreads();
@@ -258,7 +340,7 @@ struct LmsSpec {
                 constexpr int NROUND = (N + 31) & ~31;
                 for (int i = tid; i < NROUND; i += ZP) {
                     int bit = 0;
-                    if (i < N) { const int col = i / Z, k = i - col * Z; bit = soft2[col * 2 * Z + k] < 0.0f; }   // :5421
+                    if (i < N) { const int col = i / Z, k = i - col * Z; bit = soft2[col * CS + k] < 0.0f; }   // :5421
                     const unsigned w = __ballot_sync(0xffffffffu, bit);
                     if (lane == 0) {
                         if (io.hard_words) io.hard_words[(size_t)f * NWORDS + (i >> 5)] = w;

@@ -75,7 +75,7 @@ void put_array(std::ostringstream& o, const char* decl, const V& v, int n)
 } // namespace
 
 // The generated part of the translation unit: same text as tools/gen_lms_spec.py writes for the ahead-of-time instances.
-std::string lms_spec_generate(const QcHost& g, int zp, int minb)
+std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant)
 {
     std::ostringstream o;
     o << "namespace ldpcb200 { namespace gen_jit {\n";
@@ -83,7 +83,10 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb)
     put_array(o, "__constant__ int RT_COL", g.col, g.E);
     put_array(o, "__constant__ int RT_SH", g.sh, g.E);
     o << "struct Code {\n";
-    o << "    static constexpr int B = " << g.b << ", C = " << g.c << ", Z = " << g.Z << ", E = " << g.E << ", ZP = " << zp << ", MINB = " << minb << ";\n";
+    o << "    static constexpr int B = " << g.b << ", C = " << g.c << ", Z = " << g.Z << ", E = " << g.E << ", ZP = " << zp << ", MINB = " << minb
+      << ", MAXDEG = " << g.maxdeg << ";\n";
+    // variant 0: doubled columns, all check state in registers; 1: single copy, sign/position words in shared memory
+    o << "    static constexpr bool DOUBLED = " << (variant == 0 ? "true" : "false") << ", PS_SMEM = " << (variant == 0 ? "false" : "true") << ";\n";
     put_array(o, "    static constexpr int RP", g.rp, g.b + 1);
     put_array(o, "    static constexpr int COL", g.col, g.E);
     put_array(o, "    static constexpr int SH", g.sh, g.E);
@@ -102,6 +105,9 @@ bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<
     Nvrtc& n = nvrtc();
     if (!n.ok) { why = "NVRTC (libnvrtc.so.12) not found"; return false; }
     const std::string src = std::string(KERNEL_TEXT) + "\n" + gen;
+    if (const char* dump = getenv("LDPCB200_JIT_DUMP")) {          // keep the translation unit for inspection (nvcc -Xptxas -v, cuobjdump)
+        if (FILE* f = fopen(dump, "w")) { fputs(src.c_str(), f); fclose(f); }
+    }
     nvrtcProgram prog = nullptr;
     if (n.CreateProgram(&prog, src.c_str(), "lms_spec_jit.cu", 0, nullptr, nullptr) != 0) { why = "nvrtcCreateProgram failed"; return false; }
     char arch[64];
@@ -128,12 +134,12 @@ bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<
 
 // Compile (or fetch from the cache) the specialised kernel for `g` on the current device.
 // Returns nullptr and fills `why` when run-time compilation is not possible.
-const void* lms_spec_jit(const QcHost& g, int zp, int minb, std::string& why)
+const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, std::string& why)
 {
     int dev = 0;
     cudaDeviceProp prop;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { why = "no device"; return nullptr; }
-    const std::string gen = lms_spec_generate(g, zp, minb);
+    const std::string gen = lms_spec_generate(g, zp, minb, variant);
     const std::string key = std::to_string(dev) + "\n" + gen;
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);

@@ -107,7 +107,9 @@ def test_code_specialised_kernel_generates_and_compiles_without_a_gpu():
     L = load_binding()
     hd, _ = load_code("c4_wifi_12x24")
     assert L.jit_check(hd, 81) > 10000
-    hd3, _ = load_code("c3_bg1_46x68")
-    with pytest.raises(L.LdpcError) as e:                 # 46 block rows do not fit the register-state kernel
-        L.jit_check(hd3, 384)
+    big = np.full((60, 70), -1, np.int16)                # 60 block rows x Z = 1000: neither layout variant fits an SM
+    for j in range(60):
+        big[j, j] = 0; big[j, (j + 7) % 70] = 3; big[j, 65 + j % 5] = 11
+    with pytest.raises(L.LdpcError) as e:
+        L.jit_check(big, 1000)
     assert e.value.code == L.EUNSUPPORTED

@@ -97,3 +97,21 @@ def test_runtime_compiled_kernel_bit_exact(ldpc, po, code, Z, snr):
     with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=1) as d:
         assert d.kernel_info()["fast"] == 1
         assert np.array_equal(d.decode(llr, 10)["iters"], want["iters"])
+
+
+def test_large_code_variant_c3_qam64(ldpc, po):
+    """Config C3 (46 x 68 'BG1-shaped', Z = 384, QAM-64, two punctured block columns) on the second layout variant of
+    the code-specialised kernel (single-copy posteriors, sign/position words in shared memory, row weight 19 > 16)."""
+    hd, _ = load_code("c3_bg1_46x68")
+    Z = 384
+    with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=2) as d:
+        assert d.kernel_info()["fast"] == 3, d.kernel_info()
+        llr = np.concatenate([d.generate_llr(snr, 12, modulation=ldpc.MOD_QAM64, punct=2, seed=8) for snr in (0.0, 1.0, 1.5, 2.0, 2.5, 3.0, 4.0)])
+        got = d.decode(llr, 10, want_post=True)
+        sim = d.simulate(4.0, 12, 10, modulation=ldpc.MOD_QAM64, punct=2, seed=8)
+    want = po.orc_decode(po.LMS, hd, Z, llr, 10, dtype=np.float32)
+    assert len(set(want["iters"].tolist())) > 2, want["iters"]      # failures, slow and fast convergence
+    assert np.array_equal(got["iters"], want["iters"])
+    assert np.array_equal(got["hard"], want["hard"])
+    assert np.array_equal(got["post"], want["post"])
+    assert sim["frame_errors"] == int((got["hard"][72:].sum(axis=1) > 0).sum())
