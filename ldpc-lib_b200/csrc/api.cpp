@@ -23,7 +23,7 @@ cudaError_t launch_sumprod_generic(int decoder_id, const QcDev& g, const DecPara
 
 namespace ldpcb200 {
 bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant);
-std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant);
+std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, int kind);
 bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<char>& cubin, std::string& why);
 }
 
@@ -150,15 +150,19 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
         io.bp_syndrome = (uint8_t*)h->bpsynd.p;
         grid = 1;                                   // frames must follow each other, as in the reference
     }
+    if (h->decoder_id == LDPCB200_IMS_DEC) {                // energy pre-pass: the per-frame quantiser scale
+        CU(h->coef.reserve(sizeof(double) * (size_t)std::max(io.nf, 1)));
+        CU(launch_ims_energy(io, h->g.N, (double*)h->coef.p, h->stream));
+        io.coef = (const double*)h->coef.p;
+        h->last_launches++;
+    }
     bool use_fast = h->fast.ok && !(io.post && io.post_dtype != default_post_dtype(h->decoder_id, h->p.precision));
     if (use_fast && h->decoder_id == LDPCB200_LMS_DEC) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);
         CU(launch_lms_fast(h->fast, io, std::max(fgrid, 1), h->stream));
-    } else if (use_fast && h->decoder_id == LDPCB200_IMS_DEC) {
-        CU(h->coef.reserve(sizeof(double) * (size_t)std::max(io.nf, 1)));
-        int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);
-        CU(launch_ims_fast(h->fast, h->gd, h->dp, io, (double*)h->coef.p, std::max(fgrid, 1), h->stream));
-        h->last_launches++;
+    } else if (use_fast && (h->decoder_id == LDPCB200_IMS_DEC || h->decoder_id == LDPCB200_MS_DEC)) {
+        int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
+        CU(launch_ms_fast(h->fast, h->dp, io, std::max(fgrid, 1), h->stream));
     } else if (is_minsum(h->decoder_id)) {
         CU(launch_minsum_generic(h->decoder_id, h->p.precision, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, h->smem_ws, grid, h->nt, h->stream));
     } else {
@@ -302,7 +306,8 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
         CU(cudaMemset(h->bpsynd.p, 0, (size_t)h->g.R + 16));
         if (p.use_fast) {
             if (decoder_id == LDPCB200_LMS_DEC) h->fast = plan_lms_fast(h->g, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
-            else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ims_fast(h->g, h->dp, h->smem_per_sm, h->smem_per_block);
+            else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ms_fast(h->g, 2, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
+            else if (decoder_id == LDPCB200_MS_DEC) h->fast = plan_ms_fast(h->g, 1, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
         }
         return 0;
     }();
@@ -591,7 +596,7 @@ int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int
     if (!lms_spec_geometry(g, 233472, 232448, &zp, &minb, &smem, &variant)) return fail(LDPCB200_EUNSUPPORTED, "code does not suit the code-specialised kernel");
     std::vector<char> cubin;
     std::string why;
-    if (!lms_spec_compile(lms_spec_generate(g, zp, minb, variant), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());
+    if (!lms_spec_compile(lms_spec_generate(g, zp, minb, variant, 0), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());
     if (cubin_bytes) *cubin_bytes = (int)cubin.size();
     return 0;
 }

@@ -46,6 +46,59 @@ cudaError_t launch_generate_llr(const ChannelParams& ch, int N, int nf, void* ll
     return cudaGetLastError();
 }
 
+// IMS_DEC quantiser pre-pass (decoders.cpp:5472-5479): coef[f] = sqrt(N / sum_i y_i^2) with the sum taken in the
+// reference's order, i = 0 .. N-1, in double.  Floating-point addition is not associative, so the chain of one frame
+// cannot be split -- but frames are independent: one LANE per frame, 32 chains per warp, hundreds of thousands in
+// flight per launch, instead of one thread of a decoding CTA crawling through N dependent additions while the other
+// lanes of its CTA wait.  Buffer mode stages 32 frames x 32 values through shared memory so that global reads stay
+// coalesced (each lane then walks its own frame's row, padded to 33 words: no bank conflicts).
+__global__ void __launch_bounds__(128) ims_energy_kernel(FrameIO io, int N, double* __restrict__ coef)
+{
+    __shared__ double tile[4][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int f0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; f0 < io.nf; f0 += warps * 32) {
+        const int f = f0 + lane;
+        double en = 0;
+        if (io.ch.enabled) {
+            if (f < io.nf) {
+                const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
+                for (int i = 0; i < N; i++) {
+                    const double v = (double)channel_llr(io.ch, frame, i);
+                    en += v * v;
+                }
+            }
+        } else {
+            for (int base = 0; base < N; base += 32) {
+                const int i = base + lane;
+                for (int r = 0; r < 32; r++) {                     // row r = frame f0 + r, 32 consecutive values: one coalesced read
+                    double v = 0;
+                    if (f0 + r < io.nf && i < N) {
+                        const size_t k = (size_t)(f0 + r) * N + i;
+                        v = io.llr_dtype == LDPCB200_F64 ? ((const double*)io.llr)[k] : (double)((const float*)io.llr)[k];
+                    }
+                    tile[w][r][lane] = v * v;
+                }
+                __syncwarp();
+                const int m = N - base < 32 ? N - base : 32;
+                for (int j = 0; j < m; j++) en += tile[w][lane][j];
+                __syncwarp();
+            }
+        }
+        if (f < io.nf) coef[f] = sqrt(N / en);
+    }
+}
+
+cudaError_t launch_ims_energy(const FrameIO& io, int N, double* coef, cudaStream_t s)
+{
+    int warps = (io.nf + 31) / 32;
+    int grid = (warps + 3) / 4;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    ims_energy_kernel<<<grid, 128, 0, s>>>(io, N, coef);
+    return cudaGetLastError();
+}
+
 // Demodulate(), QAM_demodulator.cpp:99-566, one thread per (symbol, component)
 __global__ void demodulate_kernel(int m, int ns, double sigma, double T, int out_type,
                                   const double* __restrict__ x, double* __restrict__ res)

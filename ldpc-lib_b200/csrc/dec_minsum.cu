@@ -210,20 +210,24 @@ struct ImsGeneric {
         // formed in parallel, the additions run in the reference's order on one thread.
         __shared__ double s_sq[512];
         __shared__ double s_coef;
-        double en = 0;
-        for (int base = 0; base < N; base += 512) {
-            __syncthreads();
-            for (int i = tid; i < 512 && base + i < N; i += nt) {
-                double v = load_llr(io, N, f, base + i);
-                s_sq[i] = v * v;
+        if (io.coef) {
+            if (tid == 0) s_coef = io.coef[f];                                   // from the energy pre-pass (channel.cu)
+        } else {
+            double en = 0;
+            for (int base = 0; base < N; base += 512) {
+                __syncthreads();
+                for (int i = tid; i < 512 && base + i < N; i += nt) {
+                    double v = load_llr(io, N, f, base + i);
+                    s_sq[i] = v * v;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int m = min(512, N - base);
+                    for (int i = 0; i < m; i++) en += s_sq[i];
+                }
             }
-            __syncthreads();
-            if (tid == 0) {
-                int m = min(512, N - base);
-                for (int i = 0; i < m; i++) en += s_sq[i];
-            }
+            if (tid == 0) s_coef = sqrt(N / en);                                 // :5479
         }
-        if (tid == 0) s_coef = sqrt(N / en);                                     // :5479
         __syncthreads();
         const double coef = s_coef;
         for (int i = tid; i < N; i += nt) {                                      // :5481-5499

@@ -36,8 +36,18 @@ struct FrameIO {
     unsigned long long* counters;   // 6 x u64 (may be null): frames, frame_errors, info_bit_errors,
                                     // undetected, iter_sum, bit_errors
     unsigned char* bp_syndrome;       // R bytes: BP_DEC chained syndrome (decoders.cpp:1742-1759), or null
+    const double* coef;         // IMS_DEC: per-frame quantiser scale sqrt(N / sum y^2) from the energy pre-pass (or null)
     unsigned int* next_frame;   // work counter of the persistent grid (zeroed before the launch)
     ChannelParams ch;
+};
+
+// run-time parameters of the code-specialised flooding min-sum kernels (ms_spec.cuh)
+struct MsSpecParams {
+    float alpha;            // MS_DEC: normalisation factor
+    int ialpha;             // IMS_DEC: (int)(alpha * 16), decoders.cpp:5458
+    int max_data;           // IMS_DEC: 2^(dbits-1) - 1
+    int max_quant;          // IMS_DEC: 2^(qbits-1) - 1
+    double thr;             // IMS_DEC: quantiser threshold
 };
 
 } // namespace ldpcb200

@@ -1,14 +1,86 @@
-// Packed fixed-point min-sum throughput kernel (IMS_DEC) -- placeholder until the packed kernel lands:
-// plan_ims_fast reports "no fast kernel", so IMS_DEC handles run the table-driven kernel.
+// Host side of the code-specialised flooding min-sum kernels (ms_spec.cuh): MS_DEC in fp32 and IMS_DEC.
+// Picks an ahead-of-time instance when the matrix is a built-in one (lms_spec_aot.cu), else compiles one at run time
+// (spec_jit.cpp) when the handle allows it; otherwise the handle stays on the table-driven kernel of dec_minsum.cu.
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
 #include "kernels.h"
 
 namespace ldpcb200 {
 
-FastPlan plan_ims_fast(const QcHost&, const DecParams&, int, int) { return FastPlan(); }
+int find_lms_spec_aot(const QcHost& g, int kind);
+void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size_t* smem);
+const void* lms_spec_aot_kernel(int idx);
+const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, int kind, std::string& why);
+cudaError_t launch_ms_spec(const void* kernel, int zp, size_t smem, const FrameIO& io, const MsSpecParams& sp, int grid, cudaStream_t s);
 
-cudaError_t launch_ims_fast(const FastPlan&, const QcDev&, const DecParams&, const FrameIO&, double*, int, cudaStream_t)
+// doubled posteriors + channel values + scratch + 512 doubles of staging for the IMS energy sum
+size_t ms_spec_smem_bytes(int c, int Z)
 {
-    return cudaErrorNotSupported;
+    const size_t words = ((size_t)3 * c * Z + 4 + 1) & ~(size_t)1;
+    return 4 * words + 8 * 512;
+}
+
+bool ms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem)
+{
+    if (g.b > 32 || g.E > 512 || g.Z > 1024 || g.maxdeg > 16) return false;
+    for (int i = 0; i < g.c; i++)
+        if (g.cp[i + 1] == g.cp[i]) return false;          // pass A initialises a bit's accumulator through its first edge
+    *zp = (g.Z + 31) & ~31;
+    *smem = ms_spec_smem_bytes(g.c, g.Z);
+    if (*smem > (size_t)smem_per_block) return false;
+    const int regs = 3 * g.b + 72;
+    int m = (int)((size_t)smem_per_sm / (*smem + 1024));
+    m = std::min(m, 2048 / *zp);
+    m = std::min(m, 65536 / (*zp * regs));
+    if (m < 1) return false;
+    *minb = std::min(m, 16);
+    return true;
+}
+
+// kind: 1 = MS_DEC (precision 32 only), 2 = IMS_DEC
+FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit)
+{
+    FastPlan p;
+    if (kind == 1 && precision != 32) return p;             // the double MS_DEC stays on the bit-exact table-driven kernel
+    const char* no_spec = getenv("LDPCB200_NO_SPEC");
+    if (no_spec && *no_spec == '1') return p;
+    const int aot = find_lms_spec_aot(g, kind);
+    if (aot >= 0) {
+        int minb = 1;
+        lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);
+        if (p.smem_bytes <= (size_t)smem_per_block) {
+            p.ok = 1; p.variant = 1; p.ctas_per_sm = minb; p.spec_index = aot; p.jit_kernel = lms_spec_aot_kernel(aot);
+            return p;
+        }
+    }
+    if (allow_jit) {
+        int zp, minb;
+        size_t smem;
+        if (ms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem)) {
+            std::string why;
+            const void* k = lms_spec_jit(g, zp, minb, 0, kind, why);
+            if (k) {
+                p.ok = 1; p.variant = 2; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem; p.jit_kernel = k;
+                return p;
+            }
+            p.note = why;
+        } else
+            p.note = "code does not suit the code-specialised kernel";
+    }
+    return p;
+}
+
+cudaError_t launch_ms_fast(const FastPlan& p, const DecParams& dp, const FrameIO& io, int grid, cudaStream_t s)
+{
+    MsSpecParams sp;
+    sp.alpha = (float)dp.alpha;
+    sp.ialpha = (int)(dp.alpha * (1L << 4));                    // MS_ALPHA_FPP = 4, decoders.cpp:5458
+    sp.max_data = (short)((1L << (dp.dbits - 1)) - 1);          // :5445
+    sp.max_quant = (short)((1L << (dp.qbits - 1)) - 1);         // :5446
+    sp.thr = dp.thr;
+    return launch_ms_spec(p.jit_kernel, p.threads, p.smem_bytes, io, sp, grid, s);
 }
 
 } // namespace ldpcb200

@@ -36,15 +36,17 @@ struct FastPlan {
 };
 FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block, int allow_jit);
 cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cudaStream_t s);
-FastPlan plan_ims_fast(const QcHost& g, const DecParams& dp, int smem_per_sm, int smem_per_block);
-cudaError_t launch_ims_fast(const FastPlan& p, const QcDev& g, const DecParams& dp, const FrameIO& io,
-                            double* coef, int grid, cudaStream_t s);
+// flooding min-sum pair (ims_fast.cu -> ms_spec.cuh): kind 1 = MS_DEC fp32, 2 = IMS_DEC
+FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit);
+cudaError_t launch_ms_fast(const FastPlan& p, const DecParams& dp, const FrameIO& io, int grid, cudaStream_t s);
 
 // ---- utilities (channel.cu)
 // packed words -> one byte per bit
 cudaError_t launch_unpack_hard(const uint32_t* words, uint8_t* bytes, int nf, int N, int nwords, cudaStream_t s);
 // channel LLRs for frames [first_frame, first_frame + nf) written as F32 or F64
 cudaError_t launch_generate_llr(const ChannelParams& ch, int N, int nf, void* llr, int llr_dtype, cudaStream_t s);
+// IMS_DEC quantiser pre-pass: coef[f] = sqrt(N / sum y^2), the sum in the reference's sequential order, one lane per frame
+cudaError_t launch_ims_energy(const FrameIO& io, int N, double* coef, cudaStream_t s);
 // Demodulate / QAM_modulator at the function boundary
 cudaError_t launch_demodulate(int m, int ns, double sigma, double T, int out_type, const double* x, double* res, cudaStream_t s);
 cudaError_t launch_modulate(int m, int ns, const uint8_t* bits, double* out, cudaStream_t s);

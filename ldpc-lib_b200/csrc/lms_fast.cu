@@ -282,11 +282,11 @@ size_t lms_fast_smem(const QcHost& g)
 
 } // namespace
 
-int find_lms_spec_aot(const QcHost& g);
+int find_lms_spec_aot(const QcHost& g, int kind);
 void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size_t* smem);
 cudaError_t launch_lms_spec_aot(int idx, const FrameIO& io, int grid, cudaStream_t s);
 
-const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, std::string& why);
+const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, int kind, std::string& why);
 cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const FrameIO& io, int grid, cudaStream_t s);
 
 // launch geometry of the code-specialised kernel for g; false if the code does not suit it.
@@ -320,7 +320,7 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
     FastPlan p;
     if (precision != 32) return p;                          // the double path stays on the bit-exact table-driven kernel
     const char* no_spec = getenv("LDPCB200_NO_SPEC");
-    const int aot = (no_spec && *no_spec == '1') ? -1 : find_lms_spec_aot(g);
+    const int aot = (no_spec && *no_spec == '1') ? -1 : find_lms_spec_aot(g, 0);
     if (aot >= 0) {                                          // a code-specialised instance exists for this matrix
         int minb = 1;
         lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);
@@ -334,7 +334,7 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
         size_t smem;
         if (lms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem, &variant)) {
             std::string why;
-            const void* k = lms_spec_jit(g, zp, minb, variant, why);
+            const void* k = lms_spec_jit(g, zp, minb, variant, 0, why);
             if (k) {
                 p.ok = 1; p.variant = 2; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem;
                 p.jit_kernel = k;

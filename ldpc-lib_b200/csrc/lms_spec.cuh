@@ -99,7 +99,7 @@ struct LmsSpec {
                      "setp.ge.s32 p, %2, %5;\n\t"
                      "@p ld.shared.f32 %0, [%1+%4];\n\t"
                      "@!p ld.shared.f32 %0, [%1+%3];\n\t}"
-                     : "=f"(x) : "r"(saddr), "r"(n), "n"(4 * OFF), "n"(4 * (OFF - Z)), "n"(THR) : "memory");
+                     : "=f"(x) : "r"(saddr), "r"(n), "n"(4 * OFF), "n"(4 * (OFF - Z)), "n"(THR));
         return x;
     }
     template <int OFF, int THR>
@@ -110,6 +110,13 @@ struct LmsSpec {
                      "@p st.shared.f32 [%0+%3], %4;\n\t"
                      "@!p st.shared.f32 [%0+%2], %4;\n\t}"
                      :: "r"(saddr), "r"(n), "n"(4 * OFF), "n"(4 * (OFF - Z)), "f"(nv), "n"(THR) : "memory");
+    }
+    template <int OFF>
+    static __device__ __forceinline__ float load_plain(unsigned saddr)
+    {
+        float x;
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(saddr), "n"(4 * OFF));
+        return x;
     }
     template <int OFF>
     static __device__ __forceinline__ void store_plain(unsigned saddr, float nv)

@@ -8,12 +8,16 @@
 #include "kernels.h"
 #include "channel.cuh"
 #include "lms_spec.cuh"
+#include "ms_spec.cuh"
 
 namespace ldpcb200 {
+
+size_t ms_spec_smem_bytes(int c, int Z);
 
 struct SpecEntry {
     const char* name;
     const void* kernel;
+    int kind;                       // 0 LMS_DEC, 1 MS_DEC fp32, 2 IMS_DEC
     int b, c, Z, E, zp, minb;
     const int *rp, *col, *sh;       // host copies for matching
 };
@@ -31,7 +35,12 @@ struct SpecRegistrar {
 } // namespace ldpcb200
 
 #define LDPC_SPEC_REGISTER(NAME, B_, C_, Z_, E_, ZP_, MINB_)                                                   \
-    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)lms_spec_##NAME, B_, C_, Z_, E_, ZP_, MINB_, \
+    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)lms_spec_##NAME, 0, B_, C_, Z_, E_, ZP_, MINB_, \
+        ldpcb200::gen_##NAME::Code::RP, ldpcb200::gen_##NAME::Code::COL, ldpcb200::gen_##NAME::Code::SH});
+#define LDPC_MS_SPEC_KIND_ms 1
+#define LDPC_MS_SPEC_KIND_ims 2
+#define LDPC_MS_SPEC_REGISTER(KIND, NAME, B_, C_, Z_, E_, ZP_, MINB_)                                          \
+    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)KIND##_spec_##NAME, LDPC_MS_SPEC_KIND_##KIND, B_, C_, Z_, E_, ZP_, MINB_, \
         ldpcb200::gen_##NAME::Code::RP, ldpcb200::gen_##NAME::Code::COL, ldpcb200::gen_##NAME::Code::SH});
 
 #include "lms_spec_aot_gen.h"
@@ -39,12 +48,12 @@ struct SpecRegistrar {
 namespace ldpcb200 {
 
 // -> index of the matching ahead-of-time instance, or -1
-int find_lms_spec_aot(const QcHost& g)
+int find_lms_spec_aot(const QcHost& g, int kind)
 {
     const std::vector<SpecEntry>& r = registry();
     for (size_t k = 0; k < r.size(); k++) {
         const SpecEntry& e = r[k];
-        if (e.b != g.b || e.c != g.c || e.Z != g.Z || e.E != g.E) continue;
+        if (e.kind != kind || e.b != g.b || e.c != g.c || e.Z != g.Z || e.E != g.E) continue;
         bool same = true;
         for (int j = 0; j <= g.b && same; j++) same = e.rp[j] == g.rp[j];
         for (int i = 0; i < g.E && same; i++) same = e.col[i] == g.col[i] && e.sh[i] == g.sh[i];
@@ -60,8 +69,13 @@ void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size
     if (name) *name = e.name;
     if (threads) *threads = e.zp;
     if (minb) *minb = e.minb;
-    if (smem) *smem = sizeof(float) * (2 * (size_t)e.c * e.Z + (e.c * hw > 4 ? e.c * hw : 4));
+    if (smem) {
+        if (e.kind == 0) *smem = sizeof(float) * (2 * (size_t)e.c * e.Z + (e.c * hw > 4 ? e.c * hw : 4));
+        else *smem = ms_spec_smem_bytes(e.c, e.Z);
+    }
 }
+
+const void* lms_spec_aot_kernel(int idx) { return registry()[idx].kernel; }
 
 cudaError_t launch_lms_spec_aot(int idx, const FrameIO& io, int grid, cudaStream_t s)
 {

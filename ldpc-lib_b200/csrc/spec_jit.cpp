@@ -75,7 +75,7 @@ void put_array(std::ostringstream& o, const char* decl, const V& v, int n)
 } // namespace
 
 // The generated part of the translation unit: same text as tools/gen_lms_spec.py writes for the ahead-of-time instances.
-std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant)
+std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, int kind)
 {
     std::ostringstream o;
     o << "namespace ldpcb200 { namespace gen_jit {\n";
@@ -90,12 +90,23 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant)
     put_array(o, "    static constexpr int RP", g.rp, g.b + 1);
     put_array(o, "    static constexpr int COL", g.col, g.E);
     put_array(o, "    static constexpr int SH", g.sh, g.E);
+    {   // first edge of its block column (ascending block rows): pass A of the flooding kernels stores instead of adding
+        std::vector<int> first(g.E, 0), seen(g.c, 0);
+        for (int e = 0; e < g.E; e++) { first[e] = !seen[g.col[e]]; seen[g.col[e]] = 1; }
+        put_array(o, "    static constexpr bool FIRST", first, g.E);
+    }
     o << "    static __device__ __forceinline__ const int* rt_rp() { return RT_RP; }\n";
     o << "    static __device__ __forceinline__ const int* rt_col() { return RT_COL; }\n";
     o << "    static __device__ __forceinline__ const int* rt_sh() { return RT_SH; }\n";
     o << "};\n} }\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") lms_spec_jit(const __grid_constant__ ldpcb200::FrameIO io)\n";
-    o << "{ ldpcb200::LmsSpec<ldpcb200::gen_jit::Code>::kernel(io); }\n";
+    // kind 0: LMS_DEC (layered), 1: MS_DEC fp32 (flooding), 2: IMS_DEC (flooding, fixed point)
+    if (kind == 0) {
+        o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io)\n";
+        o << "{ ldpcb200::LmsSpec<ldpcb200::gen_jit::Code>::kernel(io); }\n";
+    } else {
+        o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)\n";
+        o << "{ ldpcb200::MsSpec<ldpcb200::gen_jit::Code, " << (kind == 2 ? "true" : "false") << ">::kernel(io, sp); }\n";
+    }
     return o.str();
 }
 
@@ -134,12 +145,12 @@ bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<
 
 // Compile (or fetch from the cache) the specialised kernel for `g` on the current device.
 // Returns nullptr and fills `why` when run-time compilation is not possible.
-const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, std::string& why)
+const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, int kind, std::string& why)
 {
     int dev = 0;
     cudaDeviceProp prop;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { why = "no device"; return nullptr; }
-    const std::string gen = lms_spec_generate(g, zp, minb, variant);
+    const std::string gen = lms_spec_generate(g, zp, minb, variant, kind);
     const std::string key = std::to_string(dev) + "\n" + gen;
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);
@@ -148,7 +159,7 @@ const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, std::st
     if (!lms_spec_compile(gen, prop.major, prop.minor, cubin, why)) return nullptr;
     Compiled c;
     cudaError_t e = cudaLibraryLoadData(&c.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&c.kernel, c.lib, "lms_spec_jit");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&c.kernel, c.lib, "spec_jit");
     if (e != cudaSuccess) { why = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
     g_cache[key] = c;
     return (const void*)c.kernel;
@@ -159,6 +170,14 @@ cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const F
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     void* args[] = { (void*)&io };
+    return cudaLaunchKernel(kernel, dim3(grid), dim3(zp), args, smem, s);
+}
+
+cudaError_t launch_ms_spec(const void* kernel, int zp, size_t smem, const FrameIO& io, const MsSpecParams& sp, int grid, cudaStream_t s)
+{
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    void* args[] = { (void*)&io, (void*)&sp };
     return cudaLaunchKernel(kernel, dim3(grid), dim3(zp), args, smem, s);
 }
 

@@ -29,23 +29,28 @@ CASES = [
     ("C1 LMS_DEC 15it fp32", "ref32x16_b", 126, "LMS", 15, 2.0, 0, 0, 32, 400000, 200),
     ("C1 LMS_DEC 15it double", "ref32x16_b", 126, "LMS", 15, 2.0, 0, 0, 64, 40000, 200),
     ("C2 LMS_DEC 10it fp32", "ref32x16_b", 256, "LMS", 10, 2.0, 0, 0, 32, 400000, 100),
+    ("C2 MS_DEC 10it fp32", "ref32x16_b", 256, "MS", 10, 3.0, 0, 0, 32, 400000, 60),
     ("C2 MS_DEC 10it double", "ref32x16_b", 256, "MS", 10, 3.0, 0, 0, 64, 20000, 60),
-    ("C3 LMS_DEC 10it QAM-64 fp32", "c3_bg1_46x68", 384, "LMS", 10, 8.0, 3, 2, 32, 4000, 20),
-    ("C3 LMS_DEC 10it QAM-64 double", "c3_bg1_46x68", 384, "LMS", 10, 8.0, 3, 2, 64, 4000, 20),
+    ("C3 LMS_DEC 10it QAM-64 fp32", "c3_bg1_46x68", 384, "LMS", 10, 1.5, 3, 2, 32, 20000, 20),
+    ("C3 LMS_DEC 10it QAM-64 double", "c3_bg1_46x68", 384, "LMS", 10, 1.5, 3, 2, 64, 4000, 20),
     ("C4 BP_DEC 20it", "c4_wifi_12x24", 81, "BP", 20, 2.0, 0, 0, 64, 40000, 100),
     ("C4 ASP_DEC 20it", "c4_wifi_12x24", 81, "ASP", 20, 2.0, 0, 0, 64, 40000, 100),
     ("C4 SP_DEC 20it", "c4_wifi_12x24", 81, "SP", 20, 2.0, 0, 0, 64, 40000, 100),
     ("C4 TASP_DEC 20it", "c4_wifi_12x24", 81, "TASP", 20, 2.0, 0, 0, 64, 40000, 100),
     ("C4 LCHE_DEC 20it", "c4_wifi_12x24", 81, "LCHE", 20, 2.0, 0, 0, 64, 40000, 60),
     ("C4 LMS_DEC 20it fp32 (NVRTC)", "c4_wifi_12x24", 81, "LMS", 20, 2.0, 0, 0, 32, 400000, 200),
-    ("C5 IMS_DEC 15it", "ref32x16_a", 126, "IMS", 15, 3.0, 0, 0, 64, 40000, 200),
+    ("C5 IMS_DEC 15it", "ref32x16_a", 126, "IMS", 15, 3.0, 0, 0, 64, 400000, 200),
+    ("C2-size IMS_DEC 10it (NVRTC)", "ref32x16_b", 256, "IMS", 10, 3.0, 0, 0, 64, 400000, 100),
     ("C5 IASP_DEC 15it", "ref32x16_a", 126, "IASP", 15, 3.0, 0, 0, 64, 40000, 100),
 ]
 
 
 def main():
     rows = []
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for label, code, Z, dec, maxiter, snr, mod, punct, prec, nf_gpu, nf_cpu in CASES:
+        if only and only not in label:
+            continue
         hd, _ = load_code(code)
         did = getattr(po, dec)
         K = (hd.shape[1] - hd.shape[0]) * Z
