@@ -121,6 +121,16 @@ __device__ __forceinline__ void pam_demod(double x, double N0, double T, int m, 
     }
 }
 
+// Four consecutive BPSK / QAM-4 LLRs 4*i4 .. 4*i4+3 from ONE Philox block (bit-identical to channel_llr() of each bit;
+// the per-bit form computes the block four times over).  Punctured positions get the puncturing value.
+__device__ __forceinline__ void channel_llr4_bpsk(const ChannelParams& ch, unsigned long long frame, int i4, float out[4])
+{
+    float z[4];
+    channel_noise4(ch, frame, (unsigned int)i4, z);
+#pragma unroll
+    for (int b = 0; b < 4; b++) out[b] = (4 * i4 + b >= ch.punct_start) ? ch.punct_value : bpsk_llr(ch, z[b]);
+}
+
 // QAM-16/64/256 LLR of bit i (kept out of line: it is heavy in registers and only used by C3-like runs)
 static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, unsigned long long frame, int i)
 {

@@ -276,7 +276,17 @@ struct LmsSpec {
                         }
                     }
                 } else {
-                    for (int i = tid; i < N; i += ZP) {
+                    for (int i4 = tid; i4 < N / 4; i4 += ZP) {                        // one Philox block -> four LLRs
+                        float o[4];
+                        channel_llr4_bpsk(io.ch, frame, i4, o);
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int i = 4 * i4 + b, col = i / Z, k = i - col * Z;
+                            soft2[col * CS + k] = o[b];
+                            if constexpr (DOUBLED) soft2[col * CS + Z + k] = o[b];
+                        }
+                    }
+                    for (int i = (N & ~3) + tid; i < N; i += ZP) {                    // tail when N is not a multiple of 4
                         const int col = i / Z, k = i - col * Z;
                         const float x = channel_llr(io.ch, frame, i);
                         soft2[col * CS + k] = x;

@@ -243,8 +243,15 @@ struct MsSpec {
                         const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
                         for (int b = 0; b < half; b++) y[i0 + b] = i0 + b >= io.ch.punct_start ? io.ch.punct_value : o[b];
                     }
-                } else
-                    for (int i = tid; i < N; i += ZP) y[i] = channel_llr(io.ch, frame, i);
+                } else {
+                    for (int i4 = tid; i4 < N / 4; i4 += ZP) {                        // one Philox block -> four LLRs
+                        float o[4];
+                        channel_llr4_bpsk(io.ch, frame, i4, o);
+#pragma unroll
+                        for (int b = 0; b < 4; b++) y[4 * i4 + b] = o[b];
+                    }
+                    for (int i = (N & ~3) + tid; i < N; i += ZP) y[i] = channel_llr(io.ch, frame, i);
+                }
             } else if (io.llr_dtype == 1) {
                 const float* src = (const float*)io.llr + (size_t)f * N;
                 for (int i = tid; i < N; i += ZP) y[i] = __ldcs(src + i);
