@@ -108,7 +108,12 @@ std::pair<double, double> bp_simulation(
     const int G = (int)eng.size();
 
     ensure_random_is_initialized();
+#ifdef LDPCB200_WITH_REFERENCE_HEADERS
+    g_next_frame = 0;       // the reference keeps no visible record of reset_random(): every call starts the stream over
+    (void)g_epoch;
+#else
     if (g_epoch != current_noise_epoch()) { g_epoch = current_noise_epoch(); g_next_frame = 0; }   // reset_random() restarts the stream
+#endif
 
     long long nse = 0, nue = 0, nde = 0, experiment = 0, decoded = 0;
     double gpu_ms = 0;

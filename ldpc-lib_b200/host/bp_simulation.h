@@ -1,7 +1,14 @@
 // bp_simulation() of the reference (bp_simulation.h:9-27, bp_simulation.cpp:305-841) on the B200 engine.
 #pragma once
 #include <utility>
+#ifdef LDPCB200_WITH_REFERENCE_HEADERS
+// Level-2 integration: this file is compiled inside ldpc-lib's own tree, against ITS matrix<T>, die()
+// and seed globals (data_structures.h:10-61, commons_portable.h)
+#include "data_structures.h"
+#include "commons_portable.h"
+#else
 #include "commons.h"
+#endif
 
 enum MODULATION_TYPE { MODULATION_SKIP = 0, MODULATION_QAM4, MODULATION_QAM16, MODULATION_QAM64, MODULATION_QAM256 };   // modulation.h:4-11
 
@@ -25,6 +32,15 @@ std::pair<double, double> bp_simulation(
     int permutation_inter,
     int punctured_blocks,
     int show_process);
+
+// The reference's QC encoder (bp_simulation.h:29-33; bp_simulation.cpp:22-192): a random codeword of the code with base
+// matrix mx (parity block columns first, uni-/bi-diagonal parity structure).  Returns 0, < 0 ("bad matrix": no positive
+// shift in the last bidiagonal column) or > 0 ("bad encoding": the structure is not one the encoder understands).
+// bp_simulation() itself transmits the all-zero codeword, as the reference does (bp_simulation.cpp:568); the search
+// drivers call this function directly to reject matrices.
+#include <vector>
+int random_codeword(matrix<int> const& mx, int tailbite_length, std::vector<bit>& codeword);
+int qc_encode(matrix<int> const& mx, int tailbite_length, std::vector<bit>& cword);
 
 // Bookkeeping of the last bp_simulation() call (an addition: the reference prints nothing comparable).
 struct bp_simulation_stats {

@@ -44,3 +44,15 @@ void ensure_random_is_initialized()
 }
 
 unsigned long long current_noise_epoch() { return noise_epoch; }
+
+// The encoder's information bits come from a host generator seeded like the reference's (commons_portable.cpp:134-166);
+// the GPU noise does not consume it.
+static std::mt19937 host_generator(1);
+static bool host_generator_seeded = false;
+int next_random_int(int minInclusive, int maxExclusive)
+{
+    ensure_random_is_initialized();
+    if (!host_generator_seeded) { host_generator = std::mt19937(initial_random_seed); host_generator_seeded = true; }
+    std::uniform_int_distribution<int> dist(minInclusive, maxExclusive - 1);
+    return dist(host_generator);
+}

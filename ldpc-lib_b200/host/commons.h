@@ -18,6 +18,20 @@ void reset_random();                      // restart the noise stream (main_simu
 void ensure_random_is_initialized();      // resolves seed 0, commons_portable.cpp:146-158
 unsigned long long current_noise_epoch(); // bumps on every reset_random(): not used for numerics
 
+int next_random_int(int minInclusive, int maxExclusive);   // host-side generator for the encoder's information bits
+
+// one bit per char, the element type of the encoder's codewords (commons_portable.h:90-109)
+struct bit {
+    char value;
+    bit() : value(0) {}
+    bit(bool that) : value(that ? 1 : 0) {}
+    bit(int that) : value(that ? 1 : 0) {}
+    bit& operator=(bool that) { value = that ? 1 : 0; return *this; }
+    bit& operator=(int that) { value = that ? 1 : 0; return *this; }
+    bit& operator^=(bit that) { value ^= that.value; return *this; }
+    operator bool() const { return value != 0; }
+};
+
 template <typename T>
 struct matrix {
 private:

@@ -191,6 +191,15 @@ def ref_bp_simulation(hd, Z, maxiter, n_frame_errors, n_experiments, snr, ref_fe
     return ber.value, fer.value
 
 
+def ref_random_codeword(hd, Z, seed):
+    """The reference's random_codeword() right after reset_random(seed): (exit code, codeword bits or None)."""
+    H = np.ascontiguousarray(hd, dtype=np.int32)
+    b, c = H.shape
+    out = np.zeros(c * Z, np.uint8)
+    rc = ref().ref_random_codeword(_ptr(H, C.c_int), b, c, Z, seed, _ptr(out, C.c_ubyte))
+    return rc, (out if rc == 0 else None)
+
+
 def sigma_bpsk(snr_db, b, c, punct=0):
     return oracle().orc_sigma_bpsk(snr_db, b, c, punct)
 

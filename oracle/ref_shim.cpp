@@ -152,6 +152,22 @@ int ref_bp_simulation(const int* H, int b, int c, int M, int max_iterations,
     return 0;
 }
 
+// random_codeword() (bp_simulation.cpp:142-192) right after reset_random() with the given seed.
+// out: c*M bytes; returns the reference's exit code (0 ok, < 0 bad matrix, > 0 bad encoding).
+int ref_random_codeword(const int* H, int b, int c, int M, int seed, unsigned char* out)
+{
+    matrix<int> HM(b, c);
+    for (int i = 0; i < b; i++)
+        for (int j = 0; j < c; j++) HM(i, j) = H[i * c + j];
+    initial_random_seed = seed;
+    reset_random();
+    std::vector<bit> cw;
+    int rc = random_codeword(HM, M, cw);
+    if (rc == 0)
+        for (size_t i = 0; i < cw.size(); i++) out[i] = (bool)cw[i];
+    return rc;
+}
+
 // n samples of the reference's N(0,1) stream (commons_portable.cpp:174-178).
 void ref_gaussian(int seed, int n, double* out)
 {

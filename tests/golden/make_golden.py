@@ -72,6 +72,22 @@ def demod():
     print("demod ok")
 
 
+def encoder():
+    """random_codeword() of the reference on the benchmark matrices (seeded): exit code and codeword."""
+    out = {}
+    for name, Z in (("ref32x16_a", 126), ("ref32x16_b", 126), ("ref32x16_b", 256), ("c4_wifi_12x24", 27), ("c3_bg1_46x68", 16)):
+        hd, _ = load_code(name)
+        hd = np.where(hd > 0, hd % Z, hd)
+        for seed in (1, 5):
+            rc, cw = po.ref_random_codeword(hd, Z, seed)
+            key = "%s_Z%d_s%d" % (name, Z, seed)
+            out[key + "_rc"] = np.int32(rc)
+            if cw is not None:
+                out[key + "_cw"] = np.packbits(cw)
+    np.savez_compressed(os.path.join(HERE, "encoder.npz"), **out)
+    print("encoder:", {k: int(v) for k, v in out.items() if k.endswith("_rc")})
+
+
 JSONX_CASES = [("basic.jsonx", ""), ("matrices.jsonx", ""), ("refs_main.jsonx", ""), ("refs_main.jsonx", "settings"),
                ("refs_main.jsonx", "settings/more"),
                ("refs_main.jsonx", "top_default"), ("refs_main.jsonx", "settings/snrs"),
@@ -112,7 +128,7 @@ def sim():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["decoders", "demod", "jsonx", "sim"]
+    what = sys.argv[1:] or ["decoders", "demod", "jsonx", "encoder", "sim"]
     po.build(ref=True)
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "refmain"])
     for w in what:

@@ -144,3 +144,25 @@ def test_sharded_frame_loop_on_device(ldpc, po):
     assert int(err.sum()) == r.nde == 40 and err[-1] == 1
     assert r.nse == int((pf[err == 1] & 0xFFFFFF).sum())
     assert fer == 40 / r.experiment
+
+
+LEVEL2 = os.path.join(ROOT, "oracle", "_ref", "main_level2")
+
+
+@pytest.mark.skipif(not os.path.exists(LEVEL2), reason="oracle/_ref/main_level2 not built (make -C oracle level2, needs /root/reference)")
+def test_level2_reference_driver_on_the_engine(tmp_path):
+    """INTEGRATION.md level 2: the reference's OWN main.cpp / main_simulation.cpp / settings.cpp (compiled from
+    /root/reference) linked against this repository's bp_simulation + decoders over libldpcb200.so.  Same input file, and
+    the FER points must agree with the reference binary's result file like the native driver's do."""
+    out = tmp_path / "out.jsonx"
+    r = subprocess.run([LEVEL2, "simulation", os.path.join(ROOT, "configs", "sim_c1_lms.jsonx"), str(out)],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, LDPCB200_JIT="0"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "girth:" in r.stdout                                   # the reference's own girth / ACE print is back in this build
+    fer, ber, txt = parse_result(out)
+    rfer, rber, rtxt = parse_result(os.path.join(ROOT, "tests", "golden", "ref_sim_c1_lms.jsonx"))
+    for p, q in zip(fer, rfer):
+        lo, hi = wilson(100, 100 / q)
+        mylo, myhi = wilson(100, 100 / p)
+        assert myhi >= lo and mylo <= hi, (p, q)
+    assert "girth_ACE = array { 16 14 17 15 }" in txt             # computed by the reference's trace_pm, unchanged
