@@ -329,7 +329,13 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
     FastPlan p;
     if (precision != 32) return p;                          // the double path stays on the bit-exact table-driven kernel
     const char* no_spec = getenv("LDPCB200_NO_SPEC");
-    const int aot = (no_spec && *no_spec == '1') ? -1 : find_lms_spec_aot(g, 0);
+    const char* no_tmem = getenv("LDPCB200_NO_TMEM");       // 1: keep the c2v messages register-compressed (lms_spec.cuh)
+    const bool tmem = !(no_tmem && *no_tmem == '1');
+    int aot = -1;
+    if (!(no_spec && *no_spec == '1')) {
+        if (tmem) aot = find_lms_spec_aot(g, 3);            // messages in tensor memory (lms_tmem.cuh)
+        if (aot < 0) aot = find_lms_spec_aot(g, 0);
+    }
     if (aot >= 0) {                                          // a code-specialised instance exists for this matrix
         int minb = 1;
         lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);

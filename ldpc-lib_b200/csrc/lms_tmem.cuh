@@ -1,0 +1,495 @@
+// Code-specialised LMS_DEC kernel (fp32) with the check-to-variable messages kept in TENSOR MEMORY.
+//
+// Same arithmetic as lms_spec.cuh / lms_fast.cu (bit-identical results to orc_lms_f32), one frame per CTA at a
+// time, lane n of the CTA = check row n of every block row.  What changes is where the decoder state lives:
+//
+//  * c2v messages -- one fp32 word per edge and lane, E*Z words per frame (128 KB at E = 128, Z = 256) -- are
+//    stored UNCOMPRESSED in the SM's tensor memory (TMEM, 512 columns x 128 lanes x 32 bit, sm_100a).  A thread
+//    owns TMEM lane 32*(warp%4)+lane and the columns [group*E, group*E + E), group = warp/4; block row J is the
+//    column range RP[J]..RP[J+1]-1.  One `tcgen05.ld.32x32b.xN` brings a whole row's old messages into
+//    registers and one `tcgen05.st` puts the new ones back: 2 instructions per ROW instead of the
+//    select / shift / xor / bit-insert bookkeeping per EDGE that the register-compressed {min1, min2, sign word,
+//    minimum flags} form of lms_spec.cuh needs (reference: prev[] {min1,min2,pos,sign} + signs[],
+//    decoders.cpp:5152-5158, 5179).  The tensor cores themselves are not used -- there is no contraction here;
+//    TMEM is the one on-chip store big enough for the messages that costs neither registers nor shared-memory
+//    bandwidth.
+//  * posteriors in shared memory, every block column stored twice back to back (2Z words) and kept in the
+//    ROTATION OF ITS LAST WRITER: after block row J updated column k through shift s, lane n holds bit
+//    (n + s) mod Z and writes it to positions n and n + Z -- two plain stores with immediate offsets, no wrap
+//    predicate; the next block row J' reads its bit (n + s') mod Z at position n + ((s' - s) mod Z), one plain
+//    load.  The rotation of every column at every point of the schedule is known at compile time (K::DELTA per
+//    edge); at iteration boundaries column k is rotated by the shift of its last block row (K::ROT), which
+//    the frame load, the syndrome windows (K::SYNSH) and the outputs take into account (K::RI = (Z - ROT) mod Z).
+//
+// Per edge-update this leaves: 1 LDS + 2 STS, 2 FADD, ~2 FMNMX (two-smallest tracking, two edges per step),
+// 1/2 LOP3 (sign parity), FSETP + SEL + LOP3 (new message) -- about half the instructions of lms_spec.cuh.
+//
+// Generated `Code` (tools/gen_lms_spec.py kind "lmst", spec_jit.cpp variant 2) adds to the lms_spec fields:
+//   static constexpr int DELTA[E], ROT[C], RI[C], SYNSH[E], TCOLS;  rt_rot() / rt_ri() / rt_synsh() __constant__ copies.
+// This header must stay free of #include (NVRTC compiles it as one string after lms_spec.cuh).
+#pragma once
+
+namespace ldpcb200 {
+
+// ---- tensor-memory plumbing (PTX ISA: tcgen05.alloc / ld / st / wait / dealloc, sm_100a)
+template <int NX> struct TmemRow;
+template <> struct TmemRow<1> {
+    static __device__ __forceinline__ void ld(unsigned t, unsigned* r)
+    { asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(t)); }
+    static __device__ __forceinline__ void st(unsigned t, const unsigned* r)
+    { asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(t), "r"(r[0]) : "memory"); }
+};
+template <> struct TmemRow<2> {
+    static __device__ __forceinline__ void ld(unsigned t, unsigned* r)
+    { asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(t)); }
+    static __device__ __forceinline__ void st(unsigned t, const unsigned* r)
+    { asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(t), "r"(r[0]), "r"(r[1]) : "memory"); }
+};
+template <> struct TmemRow<4> {
+    static __device__ __forceinline__ void ld(unsigned t, unsigned* r)
+    { asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(t)); }
+    static __device__ __forceinline__ void st(unsigned t, const unsigned* r)
+    { asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                   :: "r"(t), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory"); }
+};
+template <> struct TmemRow<8> {
+    static __device__ __forceinline__ void ld(unsigned t, unsigned* r)
+    { asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(t)); }
+    static __device__ __forceinline__ void st(unsigned t, const unsigned* r)
+    { asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   :: "r"(t), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory"); }
+};
+template <> struct TmemRow<16> {
+    static __device__ __forceinline__ void ld(unsigned t, unsigned* r)
+    { asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                     "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(t)); }
+    static __device__ __forceinline__ void st(unsigned t, const unsigned* r)
+    { asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                   :: "r"(t), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory"); }
+};
+
+// the registers of a tcgen05.ld are valid only after this wait; passing them through the statement as
+// read-write operands keeps the compiler from scheduling their first use above it
+template <int N, int I = 0>
+static __device__ __forceinline__ void tmem_touch(unsigned (&r)[N])
+{
+    if constexpr (I + 4 <= N) { asm volatile("" : "+r"(r[I]), "+r"(r[I + 1]), "+r"(r[I + 2]), "+r"(r[I + 3])); tmem_touch<N, I + 4>(r); }
+    else if constexpr (I < N) { asm volatile("" : "+r"(r[I])); tmem_touch<N, I + 1>(r); }
+}
+template <int N>
+static __device__ __forceinline__ void tmem_wait_ld(unsigned (&r)[N])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tmem_touch<N>(r);
+}
+static __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__host__ __device__ constexpr int tmem_chunk(int n) { return n >= 16 ? 16 : n >= 8 ? 8 : n >= 4 ? 4 : n >= 2 ? 2 : 1; }
+
+// N consecutive columns starting at column address t, in power-of-two pieces (13 = 8 + 4 + 1)
+template <int N, int OFF = 0>
+static __device__ __forceinline__ void tmem_ld_n(unsigned t, unsigned (&r)[N])
+{
+    if constexpr (OFF < N) {
+        constexpr int P = tmem_chunk(N - OFF);
+        TmemRow<P>::ld(t + OFF, &r[OFF]);
+        tmem_ld_n<N, OFF + P>(t, r);
+    }
+}
+template <int N, int OFF = 0>
+static __device__ __forceinline__ void tmem_st_n(unsigned t, const unsigned (&r)[N])
+{
+    if constexpr (OFF < N) {
+        constexpr int P = tmem_chunk(N - OFF);
+        TmemRow<P>::st(t + OFF, &r[OFF]);
+        tmem_st_n<N, OFF + P>(t, r);
+    }
+}
+template <int N, int OFF = 0>
+static __device__ __forceinline__ void tmem_zero_n(unsigned t)
+{
+    if constexpr (OFF < N) {
+        constexpr int P = tmem_chunk(N - OFF);
+        unsigned z[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) z[i] = 0u;
+        TmemRow<P>::st(t + OFF, z);
+        tmem_zero_n<N, OFF + P>(t);
+    }
+}
+
+template <class K>
+struct LmsTmem {
+    using S = LmsSpec<K>;
+    static constexpr int B = K::B, C = K::C, Z = K::Z, N = K::C * K::Z, R = K::B * K::Z, ZP = K::ZP, E = K::E;
+    static constexpr int HW = ZP / 32;
+    static constexpr int NB = (Z + 31) / 32;
+    static constexpr int NWORDS = (N + 31) / 32;
+    static constexpr bool ALL_ACTIVE = (Z == ZP);
+    static constexpr int CS = 2 * Z;
+    static constexpr int SOFT_WORDS = C * CS;
+    static constexpr int TCOLS = K::TCOLS;                    // power of two >= 32, >= E * ceil(warps / 4)
+    static constexpr int NWARPS = ZP / 32;
+    // shared memory (words): posteriors | packed decisions hb | syndrome edge table | row pointers | mbarrier (8-byte aligned)
+    static constexpr int HB_WORDS = C * HW > 4 ? C * HW : 4;
+    static constexpr int TAB_OFF = SOFT_WORDS + HB_WORDS;
+    static constexpr int RPW_OFF = TAB_OFF + E;
+    static constexpr int MBAR_OFF = (RPW_OFF + B + 1 + 1) & ~1;
+    static constexpr int MISC_OFF = MBAR_OFF + 2;
+    static constexpr int SMEM_WORDS = MISC_OFF + 4;
+
+    template <int J, int Q>
+    static __device__ __forceinline__ void load_soft(const float* softn, float (&sv)[K::RP[J + 1] - K::RP[J]])
+    {
+        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q < DEG) {
+            constexpr int off = K::COL[E0 + Q] * CS + K::DELTA[E0 + Q];
+            sv[Q] = softn[off];
+            load_soft<J, Q + 1>(softn, sv);
+        }
+    }
+
+    // hbw = hb + warp, lane0: this lane stores the warp's packed words
+    template <int J, int Q>
+    static __device__ __forceinline__ void phase2(float* softn, unsigned* hbw, bool lane0, bool active,
+                                                  const float (&v)[K::RP[J + 1] - K::RP[J]], float c1,
+                                                  unsigned m1x, unsigned m2x, unsigned (&msg)[K::RP[J + 1] - K::RP[J]])
+    {
+        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q < DEG) {
+            constexpr int off = K::COL[E0 + Q] * CS;
+            const bool ismin = fabsf(v[Q]) == c1;
+            const unsigned cv = (ismin ? m2x : m1x) ^ (__float_as_uint(v[Q]) & 0x80000000u);     // decoders.cpp:5193-5198
+            const float nv = v[Q] + __uint_as_float(cv);                                         // :5199-5204
+            msg[Q] = cv;
+            if (ALL_ACTIVE || active) { softn[off] = nv; softn[off + Z] = nv; }                  // lane-aligned, both copies
+            if constexpr (K::LAST[E0 + Q]) {
+                // this block row is the last one of the iteration to touch the column: its values are the
+                // iteration's posteriors, so their signs are the hard decisions the syndrome is taken of (:5281)
+                const unsigned w = __ballot_sync(0xffffffffu, (ALL_ACTIVE || active) && nv < 0.0f);
+                if (lane0) hbw[K::COL[E0 + Q] * HW] = w;
+            }
+            phase2<J, Q + 1>(softn, hbw, lane0, active, v, c1, m1x, m2x, msg);
+        }
+    }
+
+    // ---- split barrier between the loads and the stores of a layer.  A lane reads position n + DELTA of a
+    // column and writes position n, so the word one lane reads is written by ANOTHER lane of the same layer;
+    // within a warp program order protects it, across warps every warp announces "my loads are done"
+    // (mbarrier arrive, one lane per warp) and checks that all warps have (try_wait) before its first store.
+    // The loads come first in every warp, so the wait is practically never taken.
+    static __device__ __forceinline__ void loads_done(unsigned mbar, bool lane0)
+    {
+        __syncwarp();
+        if (lane0) asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(mbar) : "memory");
+    }
+    static __device__ __forceinline__ void wait_loads(unsigned mbar, unsigned parity)
+    {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "WAIT_LOADS:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                     "@!p bra WAIT_LOADS;\n\t}" :: "r"(mbar), "r"(parity) : "memory");
+    }
+
+    template <int J>
+    static __device__ __forceinline__ void layer(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active)
+    {
+        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+        unsigned msg[DEG];
+        float sv[DEG], v[DEG];
+        tmem_ld_n<DEG>(trow + E0, msg);                                                          // old c2v of this row
+        load_soft<J, 0>(softn, sv);
+        tmem_wait_ld<DEG>(msg);
+#pragma unroll
+        for (int q = 0; q < DEG; q++) v[q] = sv[q] - __uint_as_float(msg[q]);                    // :5152-5158
+        loads_done(mbar, lane0);
+        typename S::RowAcc a;
+        a.c1 = __int_as_float(0x7f800000); a.c2 = a.c1;
+        unsigned sacc = 0;
+        S::template reduce<J, 0>(v, a, sacc);
+        const float n1 = fminf(fmaxf(a.c1 - 0.4f, 0.0f), 32767.0f);                              // :5166-5168, :5131-5137
+        const float n2 = fminf(fmaxf(a.c2 - 0.4f, 0.0f), 32767.0f);
+        const unsigned rs = sacc & 0x80000000u;
+        const unsigned m1x = __float_as_uint(n1) ^ rs, m2x = __float_as_uint(n2) ^ rs;
+        if constexpr (B % 2 == 0) wait_loads(mbar, J & 1);
+        else { wait_loads(mbar, ph); ph ^= 1u; }
+        phase2<J, 0>(softn, hbw, lane0, active, v, a.c1, m1x, m2x, msg);
+        tmem_st_n<DEG>(trow + E0, msg);                                                          // :5179
+    }
+
+    template <int J>
+    static __device__ __forceinline__ void layers(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active)
+    {
+        if constexpr (J < B) {
+            layer<J>(softn, hbw, trow, mbar, ph, lane0, active);
+            __syncthreads();
+            layers<J + 1>(softn, hbw, trow, mbar, ph, lane0, active);
+        }
+    }
+
+    // ---- syndrome of the hard decisions on packed bits.  hb[col * HW + w] = signs of positions 32w..32w+31 of
+    // column col (the column's rotated order).  During the iterations the words are written by the layers
+    // themselves (phase2, K::LAST edges); pack() builds them for the channel values before the first iteration.
+    static __device__ __forceinline__ void pack(const float* soft2, unsigned* hb, int tid)
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll 8
+        for (int col = 0; col < C; col++) {
+            const int bit = (ALL_ACTIVE || tid < Z) ? soft2[col * CS + tid] < 0.0f : 0;
+            const unsigned w = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) hb[col * HW + warp] = w;
+        }
+        __syncthreads();
+    }
+
+    // One task = 32 check rows (block row j, word w): XOR over the row's edges of the 32-bit window of the
+    // edge's column that starts at bit 32w + SYNSH.  Four lanes share a task (edges q, q+4, ...), 8 tasks per warp;
+    // tab[e] = column word offset | SYNSH << 16 and rpw[] = row pointers are shared-memory copies so that lanes
+    // working on different rows do not serialise on the constant cache.
+    static __device__ __forceinline__ int syndrome(const unsigned* hb, const unsigned* tab, const unsigned* rpw, int tid)
+    {
+        const int lane = tid & 31, warp = tid >> 5, q = lane & 3;
+        constexpr int NT = B * NB, STEP = 8 * NWARPS, ROUNDS = (NT + STEP - 1) / STEP;
+        unsigned bad = 0;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            const int t = r * STEP + warp * 8 + (lane >> 2);
+            unsigned acc = 0;
+            int w = 0;
+            if (t < NT) {
+                const int j = t / NB;
+                w = t - j * NB;
+                const int e1 = (int)rpw[j + 1];
+                for (int e = (int)rpw[j] + q; e < e1; e += 4) {
+                    const unsigned pk = tab[e];
+                    const unsigned* hc = hb + (pk & 0xffffu);
+                    int start = 32 * w + (int)(pk >> 16);
+                    if (start >= Z) start -= Z;
+                    const int i0 = start >> 5, i1 = i0 + 1 < HW ? i0 + 1 : HW - 1;
+                    unsigned win = __funnelshift_r(hc[i0], hc[i1], start & 31);
+                    if constexpr (Z % 32 != 0 || true) {
+                        const int nvalid = Z - start;
+                        if (nvalid < 32) win = (win & ((1u << nvalid) - 1u)) | (hc[0] << nvalid);
+                    }
+                    acc ^= win;
+                }
+            }
+            acc ^= __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc ^= __shfl_xor_sync(0xffffffffu, acc, 2);
+            const int lanes = Z - 32 * w;
+            if (lanes < 32) acc &= (1u << lanes) - 1u;
+            bad |= acc;
+        }
+        return __syncthreads_or(bad != 0);
+    }
+
+    // position of bit k of block column col in the doubled column (first copy)
+    static __device__ __forceinline__ int pos_of(int col, int k)
+    {
+        int p = k + K::rt_ri()[col];
+        return p >= Z ? p - Z : p;
+    }
+    static __device__ __forceinline__ void put(float* soft2, int col, int k, float x)
+    {
+        const int p = col * CS + pos_of(col, k);
+        soft2[p] = x;
+        soft2[p + Z] = x;
+    }
+
+    static __device__ __forceinline__ void kernel(const FrameIO& io)
+    {
+        extern __shared__ __align__(16) float soft2[];
+        unsigned* hb = (unsigned*)(soft2 + SOFT_WORDS);
+        unsigned* tab = (unsigned*)(soft2 + TAB_OFF);
+        unsigned* rpw = (unsigned*)(soft2 + RPW_OFF);
+        int* s_misc = (int*)(soft2 + MISC_OFF);
+        const int tid = threadIdx.x;
+        const bool active = tid < Z;
+        const bool lane0 = (tid & 31) == 0;
+        const bool noexit = io.flags & 8u;                       // LDPCB200_NO_EARLY_EXIT
+        float* softn = soft2 + tid;
+        unsigned* hbw = hb + (tid >> 5);
+        const unsigned mbar = (unsigned)__cvta_generic_to_shared(soft2 + MBAR_OFF);
+        unsigned ph = 0;
+        for (int e = tid; e < E; e += ZP) tab[e] = (unsigned)(K::rt_col()[e] * HW) | ((unsigned)K::rt_synsh()[e] << 16);
+        for (int j = tid; j <= B; j += ZP) rpw[j] = (unsigned)K::rt_rp()[j];
+        if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"((unsigned)NWARPS) : "memory");
+
+        // tensor memory: one warp allocates TCOLS columns for the CTA and frees them at the end
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"((unsigned)__cvta_generic_to_shared(hb)), "r"((unsigned)TCOLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned tbase = *(volatile unsigned*)hb;
+        // this thread's lane (bits 31:16) and first column (bits 15:0)
+        const unsigned trow = tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * E);
+
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) { s_misc[0] = (int)atomicAdd(io.next_frame, 1u); s_misc[1] = 0; s_misc[2] = 0; }
+            __syncthreads();
+            const int f = s_misc[0];
+            if (f >= io.nf) break;
+
+            if (io.ch.enabled) {
+                const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
+                if (io.ch.m > 2) {
+                    // QAM-16/64/256: one thread per PAM component, m/2 LLRs from one demodulation
+                    const int half = io.ch.m >> 1, ncomp = 2 * (N / io.ch.m);
+                    for (int c = tid; c < ncomp; c += ZP) {
+                        float o[4];
+                        channel_llr_qam_component(io.ch, frame, c, o);
+                        const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
+                        for (int b = 0; b < half; b++) {
+                            const int i = i0 + b, col = i / Z, k = i - col * Z;
+                            put(soft2, col, k, i >= io.ch.punct_start ? io.ch.punct_value : o[b]);
+                        }
+                    }
+                } else {
+                    for (int i4 = tid; i4 < N / 4; i4 += ZP) {                        // one Philox block -> four LLRs
+                        float o[4];
+                        channel_llr4_bpsk(io.ch, frame, i4, o);
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int i = 4 * i4 + b, col = i / Z, k = i - col * Z;
+                            put(soft2, col, k, o[b]);
+                        }
+                    }
+                    for (int i = (N & ~3) + tid; i < N; i += ZP) {                    // tail when N is not a multiple of 4
+                        const int col = i / Z, k = i - col * Z;
+                        put(soft2, col, k, channel_llr(io.ch, frame, i));
+                    }
+                }
+            } else if (io.llr_dtype == 1) {                      // LDPCB200_F32
+                const float* y = (const float*)io.llr + (size_t)f * N;
+                if (ALL_ACTIVE || active) {
+#pragma unroll 8
+                    for (int col = 0; col < C; col++) {          // position tid of column col holds bit (tid + ROT) mod Z
+                        int k = tid + K::rt_rot()[col];
+                        if (k >= Z) k -= Z;
+                        const float x = __ldcs(y + col * Z + k);
+                        softn[col * CS] = x;
+                        softn[col * CS + Z] = x;
+                    }
+                }
+            } else {
+                const double* y = (const double*)io.llr + (size_t)f * N;
+                if (ALL_ACTIVE || active) {
+#pragma unroll 8
+                    for (int col = 0; col < C; col++) {
+                        int k = tid + K::rt_rot()[col];
+                        if (k >= Z) k -= Z;
+                        const float x = (float)__ldcs(y + col * Z + k);
+                        softn[col * CS] = x;
+                        softn[col * CS + Z] = x;
+                    }
+                }
+            }
+            tmem_zero_n<E>(trow);                                                       // prev[] = 0, decoders.cpp:5088-5108
+            tmem_wait_st();
+            __syncthreads();
+
+            pack(soft2, hb, tid);
+            int parity = syndrome(hb, tab, rpw, tid);                                   // :5111-5115
+            int ret = 0, locked = 0, iter;
+            if (!parity) { ret = 1; locked = 1; }
+            for (iter = 0; iter < io.maxiter; iter++) {
+                if (!parity && !noexit) break;                                          // :5119
+                tmem_wait_st();                                                         // last iteration's messages are in place
+                layers<0>(softn, hbw, trow, mbar, ph, lane0, active);
+                parity = syndrome(hb, tab, rpw, tid);                                   // :5281-5284
+                if (!parity && !locked) { ret = iter + 1; locked = 1; }
+                if (!parity && !noexit) break;
+            }
+            if (!locked) ret = parity ? -iter : iter + 1;                               // :5424
+
+            if (io.post) {
+                if (io.post_dtype == 1) {
+                    float* p = (float*)io.post + (size_t)f * N;
+                    for (int col = 0; col < C; col++)
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = soft2[col * CS + tid + K::rt_ri()[col]];
+                } else {
+                    double* p = (double*)io.post + (size_t)f * N;
+                    for (int col = 0; col < C; col++)
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = (double)soft2[col * CS + tid + K::rt_ri()[col]];
+                }
+            }
+            // hb holds the packed decisions of the final posteriors (:5421).  Error counts are popcounts -- the
+            // rotation of a column does not matter for them; bits >= R are information bits (bp_simulation.cpp:738),
+            // i.e. the block columns >= B
+            {
+                const int lane = tid & 31;
+                int nerr = 0, nerr_info = 0;
+                for (int t = tid; t < ((C * HW + 31) & ~31); t += ZP) {
+                    const unsigned w = t < C * HW ? hb[t] : 0u;
+                    const int pc = __popc(w);
+                    nerr += pc;
+                    if (t >= B * HW) nerr_info += pc;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    nerr += __shfl_xor_sync(0xffffffffu, nerr, o);
+                    nerr_info += __shfl_xor_sync(0xffffffffu, nerr_info, o);
+                }
+                if (lane == 0 && nerr) { atomicAdd(&s_misc[1], nerr); atomicAdd(&s_misc[2], nerr_info); }
+                if (io.hard_words) {
+                    unsigned* out = io.hard_words + (size_t)f * NWORDS;
+                    if constexpr (Z % 32 == 0) {
+                        // output word g = bits k0..k0+31 of one column = positions (k0 + RI) mod Z ...: a 32-bit window of hb
+                        for (int g = tid; g < NWORDS; g += ZP) {
+                            const int col = g / HW, k0 = 32 * (g - col * HW);
+                            int start = k0 + K::rt_ri()[col];
+                            if (start >= Z) start -= Z;
+                            const unsigned* hc = hb + col * HW;
+                            const int i0 = start >> 5, i1 = i0 + 1 < HW ? i0 + 1 : 0;
+                            out[g] = __funnelshift_r(hc[i0], hc[i1], start & 31);
+                        }
+                    } else {
+                        constexpr int NROUND = (N + 31) & ~31;
+                        for (int i = tid; i < NROUND; i += ZP) {
+                            int bit = 0;
+                            if (i < N) { const int col = i / Z, k = i - col * Z; bit = soft2[col * CS + k + K::rt_ri()[col]] < 0.0f; }
+                            const unsigned w = __ballot_sync(0xffffffffu, bit);
+                            if (lane == 0) out[i >> 5] = w;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const int e = s_misc[1], ei = s_misc[2];
+                    if (io.iters) io.iters[f] = ret;
+                    if (io.per_frame)
+                        io.per_frame[f] = (e ? 0x80000000u : 0u) | (ret >= 0 ? 0x40000000u : 0u) | (unsigned)(ei < 0xFFFFFF ? ei : 0xFFFFFF);
+                    if (io.counters) {
+                        atomicAdd(&io.counters[0], 1ull);
+                        atomicAdd(&io.counters[4], (unsigned long long)(ret < 0 ? -ret : ret));
+                        if (e) {
+                            atomicAdd(&io.counters[1], 1ull);
+                            atomicAdd(&io.counters[2], (unsigned long long)ei);
+                            atomicAdd(&io.counters[5], (unsigned long long)e);
+                            if (ret >= 0) atomicAdd(&io.counters[3], 1ull);
+                        }
+                    }
+                }
+            }
+        }
+
+        // every thread's TMEM traffic is complete (wait::ld / wait::st above); hand the columns back
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)TCOLS) : "memory");
+        }
+    }
+};
+
+} // namespace ldpcb200
