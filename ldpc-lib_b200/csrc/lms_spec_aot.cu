@@ -15,12 +15,13 @@ namespace ldpcb200 {
 
 size_t ms_spec_smem_bytes(int c, int Z);
 
-// shared memory of LmsTmem<K> (lms_tmem.cuh, SMEM_WORDS): posteriors | packed decisions | edge table | row pointers | mbarrier | misc
-size_t lms_tmem_smem_bytes(int b, int c, int Z, int E)
+// shared memory of LmsTmem<K> (lms_tmem.cuh, SMEM_WORDS): posteriors | packed decisions | syndrome plan | mbarrier | misc
+size_t lms_tmem_smem_bytes(int b, int c, int Z, int maxdeg)
 {
-    const int zp = (Z + 31) / 32 * 32, hw = zp / 32;
-    const size_t soft = 2 * (size_t)c * Z, hb = (size_t)(c * hw > 4 ? c * hw : 4);
-    const size_t mbar = (soft + hb + E + b + 1 + 1) & ~(size_t)1;
+    const int zp = (Z + 31) / 32 * 32, hw = zp / 32, nb = (Z + 31) / 32, nwarps = zp / 32;
+    const size_t soft = 2 * (size_t)c * Z, hb = (size_t)(c * hw > 3 ? c * hw : 3) + 1;
+    const size_t plan = (size_t)((b * nb + 8 * nwarps - 1) / (8 * nwarps)) * ((maxdeg + 3) / 4) * zp;
+    const size_t mbar = (soft + hb + plan + 1) & ~(size_t)1;
     return sizeof(float) * (mbar + 2 + 4);
 }
 
@@ -35,7 +36,7 @@ struct SpecEntry {
     const char* name;
     const void* kernel;
     int kind;                       // 0 LMS_DEC, 1 MS_DEC fp32, 2 IMS_DEC, 3 LMS_DEC with the messages in tensor memory
-    int b, c, Z, E, zp, minb;
+    int b, c, Z, E, zp, minb, maxdeg;
     const int *rp, *col, *sh;       // host copies for matching
 };
 
@@ -52,13 +53,13 @@ struct SpecRegistrar {
 } // namespace ldpcb200
 
 #define LDPC_SPEC_REGISTER(NAME, B_, C_, Z_, E_, ZP_, MINB_)                                                   \
-    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)lms_spec_##NAME, 0, B_, C_, Z_, E_, ZP_, MINB_, \
+    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)lms_spec_##NAME, 0, B_, C_, Z_, E_, ZP_, MINB_, ldpcb200::gen_##NAME::Code::MAXDEG, \
         ldpcb200::gen_##NAME::Code::RP, ldpcb200::gen_##NAME::Code::COL, ldpcb200::gen_##NAME::Code::SH});
 #define LDPC_MS_SPEC_KIND_ms 1
 #define LDPC_MS_SPEC_KIND_ims 2
 #define LDPC_MS_SPEC_KIND_lmst 3
 #define LDPC_MS_SPEC_REGISTER(KIND, NAME, B_, C_, Z_, E_, ZP_, MINB_)                                          \
-    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)KIND##_spec_##NAME, LDPC_MS_SPEC_KIND_##KIND, B_, C_, Z_, E_, ZP_, MINB_, \
+    static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)KIND##_spec_##NAME, LDPC_MS_SPEC_KIND_##KIND, B_, C_, Z_, E_, ZP_, MINB_, ldpcb200::gen_##NAME::Code::MAXDEG, \
         ldpcb200::gen_##NAME::Code::RP, ldpcb200::gen_##NAME::Code::COL, ldpcb200::gen_##NAME::Code::SH});
 
 #include "lms_spec_aot_gen.h"
@@ -89,7 +90,7 @@ void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size
     if (minb) *minb = e.minb;
     if (smem) {
         if (e.kind == 0) *smem = sizeof(float) * (2 * (size_t)e.c * e.Z + (e.c * hw > 4 ? e.c * hw : 4));
-        else if (e.kind == 3) *smem = lms_tmem_smem_bytes(e.b, e.c, e.Z, e.E);
+        else if (e.kind == 3) *smem = lms_tmem_smem_bytes(e.b, e.c, e.Z, e.maxdeg);
         else *smem = ms_spec_smem_bytes(e.c, e.Z);
         // tensor-memory variant: exactly `minb` CTAs may share an SM (their TMEM columns add up to 512; one more
         // resident CTA would sit in tcgen05.alloc until another exits), so the request is padded until minb + 1

@@ -134,11 +134,11 @@ struct LmsTmem {
     static constexpr int SOFT_WORDS = C * CS;
     static constexpr int TCOLS = K::TCOLS;                    // power of two >= 32, >= E * ceil(warps / 4)
     static constexpr int NWARPS = ZP / 32;
-    // shared memory (words): posteriors | packed decisions hb | syndrome edge table | row pointers | mbarrier (8-byte aligned)
-    static constexpr int HB_WORDS = C * HW > 4 ? C * HW : 4;
-    static constexpr int TAB_OFF = SOFT_WORDS + HB_WORDS;
-    static constexpr int RPW_OFF = TAB_OFF + E;
-    static constexpr int MBAR_OFF = (RPW_OFF + B + 1 + 1) & ~1;
+    // shared memory (words): posteriors | packed decisions hb (+ one zero word) | syndrome plan | mbarrier (8-byte aligned) | misc
+    static constexpr int HB_WORDS = (C * HW > 3 ? C * HW : 3) + 1;
+    static constexpr int PLAN_OFF = SOFT_WORDS + HB_WORDS;
+    static constexpr int PLAN_WORDS = ((B * NB + 8 * NWARPS - 1) / (8 * NWARPS)) * ((K::MAXDEG + 3) / 4) * ZP;
+    static constexpr int MBAR_OFF = (PLAN_OFF + PLAN_WORDS + 1) & ~1;
     static constexpr int MISC_OFF = MBAR_OFF + 2;
     static constexpr int SMEM_WORDS = MISC_OFF + 4;
 
@@ -195,6 +195,36 @@ struct LmsTmem {
                      "@!p bra WAIT_LOADS;\n\t}" :: "r"(mbar), "r"(parity) : "memory");
     }
 
+    // two smallest magnitudes of v[LO..HI): balanced tree (depth log2 instead of the linear chain of S::reduce) so that
+    // the few warps of an SM find independent instructions; min / max only, hence exact and order independent
+    template <int DEG, int LO, int HI>
+    static __device__ __forceinline__ typename S::RowAcc two_smallest(const float (&v)[DEG])
+    {
+        typename S::RowAcc r;
+        if constexpr (HI - LO == 1) {
+            r.c1 = fabsf(v[LO]); r.c2 = __int_as_float(0x7f800000);
+        } else if constexpr (HI - LO == 2) {
+            r.c1 = fminf(fabsf(v[LO]), fabsf(v[LO + 1])); r.c2 = fmaxf(fabsf(v[LO]), fabsf(v[LO + 1]));
+        } else {
+            constexpr int MID = LO + (((HI - LO) / 2 + 1) & ~1);         // even-sized left half
+            const typename S::RowAcc a = two_smallest<DEG, LO, MID>(v), b = two_smallest<DEG, MID, HI>(v);
+            r.c1 = fminf(a.c1, b.c1);
+            r.c2 = fminf(fminf(a.c2, b.c2), fmaxf(a.c1, b.c1));
+        }
+        return r;
+    }
+    template <int DEG, int LO, int HI>
+    static __device__ __forceinline__ unsigned sign_xor(const float (&v)[DEG])
+    {
+        if constexpr (HI - LO == 1) return __float_as_uint(v[LO]);
+        else if constexpr (HI - LO == 2) return __float_as_uint(v[LO]) ^ __float_as_uint(v[LO + 1]);
+        else if constexpr (HI - LO == 3) return __float_as_uint(v[LO]) ^ __float_as_uint(v[LO + 1]) ^ __float_as_uint(v[LO + 2]);
+        else {
+            constexpr int T = (HI - LO) / 3;
+            return sign_xor<DEG, LO, LO + T>(v) ^ sign_xor<DEG, LO + T, LO + 2 * T>(v) ^ sign_xor<DEG, LO + 2 * T, HI>(v);
+        }
+    }
+
     template <int J>
     static __device__ __forceinline__ void layer(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active)
     {
@@ -207,10 +237,8 @@ struct LmsTmem {
 #pragma unroll
         for (int q = 0; q < DEG; q++) v[q] = sv[q] - __uint_as_float(msg[q]);                    // :5152-5158
         loads_done(mbar, lane0);
-        typename S::RowAcc a;
-        a.c1 = __int_as_float(0x7f800000); a.c2 = a.c1;
-        unsigned sacc = 0;
-        S::template reduce<J, 0>(v, a, sacc);
+        const typename S::RowAcc a = two_smallest<DEG, 0, DEG>(v);
+        const unsigned sacc = sign_xor<DEG, 0, DEG>(v);
         const float n1 = fminf(fmaxf(a.c1 - 0.4f, 0.0f), 32767.0f);                              // :5166-5168, :5131-5137
         const float n2 = fminf(fmaxf(a.c2 - 0.4f, 0.0f), 32767.0f);
         const unsigned rs = sacc & 0x80000000u;
@@ -247,41 +275,62 @@ struct LmsTmem {
     }
 
     // One task = 32 check rows (block row j, word w): XOR over the row's edges of the 32-bit window of the
-    // edge's column that starts at bit 32w + SYNSH.  Four lanes share a task (edges q, q+4, ...), 8 tasks per warp;
-    // tab[e] = column word offset | SYNSH << 16 and rpw[] = row pointers are shared-memory copies so that lanes
-    // working on different rows do not serialise on the constant cache.
-    static __device__ __forceinline__ int syndrome(const unsigned* hb, const unsigned* tab, const unsigned* rpw, int tid)
+    // edge's column that starts at bit 32w + SYNSH.  Four lanes share a task (edges q, q+4, ...), 8 tasks per warp,
+    // SYN_ROUNDS rounds.  What a thread has to fetch for each of its (task, edge) pairs never changes, so it is
+    // worked out once per CTA (build_plan) into one word per pair:
+    //   bits 0-9 column word offset in hb | 10-14 first word | 15-19 second word | 20-24 bit shift | 25-30 valid bits
+    // (a pair that does not exist points at the always-zero word hb[HB_WORDS - 1]).
+    static constexpr int SYN_NT = B * NB, SYN_STEP = 8 * NWARPS, SYN_ROUNDS = (SYN_NT + SYN_STEP - 1) / SYN_STEP;
+    static constexpr int SYN_QE = (K::MAXDEG + 3) / 4;
+
+    static __device__ __forceinline__ void build_plan(unsigned* plan, int tid)
     {
         const int lane = tid & 31, warp = tid >> 5, q = lane & 3;
-        constexpr int NT = B * NB, STEP = 8 * NWARPS, ROUNDS = (NT + STEP - 1) / STEP;
+        for (int r = 0; r < SYN_ROUNDS; r++) {
+            const int t = r * SYN_STEP + warp * 8 + (lane >> 2);
+            for (int i = 0; i < SYN_QE; i++) {
+                unsigned pk = (unsigned)(HB_WORDS - 1) | (32u << 25);
+                if (t < SYN_NT) {
+                    const int j = t / NB, w = t - j * NB;
+                    const int e = K::rt_rp()[j] + q + 4 * i;
+                    if (e < K::rt_rp()[j + 1]) {
+                        int start = 32 * w + K::rt_synsh()[e];
+                        if (start >= Z) start -= Z;
+                        const int i0 = start >> 5, i1 = i0 + 1 < HW ? i0 + 1 : (Z % 32 == 0 ? 0 : HW - 1);
+                        const int nvalid = Z - start < 32 ? Z - start : 32;
+                        pk = (unsigned)(K::rt_col()[e] * HW) | ((unsigned)i0 << 10) | ((unsigned)i1 << 15) | ((unsigned)(start & 31) << 20)
+                             | ((unsigned)nvalid << 25);
+                    }
+                }
+                plan[(r * SYN_QE + i) * ZP + tid] = pk;
+            }
+        }
+    }
+
+    static __device__ __forceinline__ int syndrome(const unsigned* hb, const unsigned* plan, int tid)
+    {
         unsigned bad = 0;
 #pragma unroll
-        for (int r = 0; r < ROUNDS; r++) {
-            const int t = r * STEP + warp * 8 + (lane >> 2);
+        for (int r = 0; r < SYN_ROUNDS; r++) {
             unsigned acc = 0;
-            int w = 0;
-            if (t < NT) {
-                const int j = t / NB;
-                w = t - j * NB;
-                const int e1 = (int)rpw[j + 1];
-                for (int e = (int)rpw[j] + q; e < e1; e += 4) {
-                    const unsigned pk = tab[e];
-                    const unsigned* hc = hb + (pk & 0xffffu);
-                    int start = 32 * w + (int)(pk >> 16);
-                    if (start >= Z) start -= Z;
-                    const int i0 = start >> 5, i1 = i0 + 1 < HW ? i0 + 1 : HW - 1;
-                    unsigned win = __funnelshift_r(hc[i0], hc[i1], start & 31);
-                    if constexpr (Z % 32 != 0 || true) {
-                        const int nvalid = Z - start;
-                        if (nvalid < 32) win = (win & ((1u << nvalid) - 1u)) | (hc[0] << nvalid);
-                    }
-                    acc ^= win;
+#pragma unroll
+            for (int i = 0; i < SYN_QE; i++) {
+                const unsigned pk = plan[(r * SYN_QE + i) * ZP + tid];
+                const unsigned* hc = hb + (pk & 1023u);
+                unsigned win = __funnelshift_r(hc[(pk >> 10) & 31u], hc[(pk >> 15) & 31u], pk >> 20);     // shift uses the low 5 bits
+                if constexpr (Z % 32 != 0) {
+                    const unsigned nvalid = (pk >> 25) & 63u;       // the window runs over the end of the column: the rest wraps to bit 0
+                    if (nvalid < 32u) win = (win & ((1u << nvalid) - 1u)) | (hc[0] << nvalid);
                 }
+                acc ^= win;
             }
             acc ^= __shfl_xor_sync(0xffffffffu, acc, 1);
             acc ^= __shfl_xor_sync(0xffffffffu, acc, 2);
-            const int lanes = Z - 32 * w;
-            if (lanes < 32) acc &= (1u << lanes) - 1u;
+            if constexpr (Z % 32 != 0) {
+                const int t = r * SYN_STEP + (tid >> 5) * 8 + ((tid & 31) >> 2);
+                const int lanes = Z - 32 * (t % NB);
+                if (lanes < 32) acc &= (1u << lanes) - 1u;
+            }
             bad |= acc;
         }
         return __syncthreads_or(bad != 0);
@@ -304,8 +353,7 @@ struct LmsTmem {
     {
         extern __shared__ __align__(16) float soft2[];
         unsigned* hb = (unsigned*)(soft2 + SOFT_WORDS);
-        unsigned* tab = (unsigned*)(soft2 + TAB_OFF);
-        unsigned* rpw = (unsigned*)(soft2 + RPW_OFF);
+        unsigned* plan = (unsigned*)(soft2 + PLAN_OFF);
         int* s_misc = (int*)(soft2 + MISC_OFF);
         const int tid = threadIdx.x;
         const bool active = tid < Z;
@@ -315,8 +363,8 @@ struct LmsTmem {
         unsigned* hbw = hb + (tid >> 5);
         const unsigned mbar = (unsigned)__cvta_generic_to_shared(soft2 + MBAR_OFF);
         unsigned ph = 0;
-        for (int e = tid; e < E; e += ZP) tab[e] = (unsigned)(K::rt_col()[e] * HW) | ((unsigned)K::rt_synsh()[e] << 16);
-        for (int j = tid; j <= B; j += ZP) rpw[j] = (unsigned)K::rt_rp()[j];
+        build_plan(plan, tid);
+        if (tid == 0) hb[HB_WORDS - 1] = 0u;
         if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"((unsigned)NWARPS) : "memory");
 
         // tensor memory: one warp allocates TCOLS columns for the CTA and frees them at the end
@@ -330,7 +378,8 @@ struct LmsTmem {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned tbase = *(volatile unsigned*)hb;
         // this thread's lane (bits 31:16) and first column (bits 15:0)
-        const unsigned trow = tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * E);
+        // (the shuffle tells the compiler that the address is warp-uniform: LDTM / STTM take it from a uniform register)
+        const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * E), 0);
 
         for (;;) {
             __syncthreads();
@@ -371,13 +420,23 @@ struct LmsTmem {
             } else if (io.llr_dtype == 1) {                      // LDPCB200_F32
                 const float* y = (const float*)io.llr + (size_t)f * N;
                 if (ALL_ACTIVE || active) {
-#pragma unroll 8
-                    for (int col = 0; col < C; col++) {          // position tid of column col holds bit (tid + ROT) mod Z
-                        int k = tid + K::rt_rot()[col];
-                        if (k >= Z) k -= Z;
-                        const float x = __ldcs(y + col * Z + k);
-                        softn[col * CS] = x;
-                        softn[col * CS + Z] = x;
+#pragma unroll
+                    for (int c0 = 0; c0 < C; c0 += 16) {         // 16 loads in flight per thread
+                        float x[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {           // position tid of column col holds bit (tid + ROT) mod Z
+                            const int col = c0 + u;
+                            if (col < C) {
+                                int k = tid + K::rt_rot()[col];
+                                if (k >= Z) k -= Z;
+                                x[u] = __ldcs(y + col * Z + k);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            const int col = c0 + u;
+                            if (col < C) { softn[col * CS] = x[u]; softn[col * CS + Z] = x[u]; }
+                        }
                     }
                 }
             } else {
@@ -398,14 +457,14 @@ struct LmsTmem {
             __syncthreads();
 
             pack(soft2, hb, tid);
-            int parity = syndrome(hb, tab, rpw, tid);                                   // :5111-5115
+            int parity = syndrome(hb, plan, tid);                                   // :5111-5115
             int ret = 0, locked = 0, iter;
             if (!parity) { ret = 1; locked = 1; }
             for (iter = 0; iter < io.maxiter; iter++) {
                 if (!parity && !noexit) break;                                          // :5119
                 tmem_wait_st();                                                         // last iteration's messages are in place
                 layers<0>(softn, hbw, trow, mbar, ph, lane0, active);
-                parity = syndrome(hb, tab, rpw, tid);                                   // :5281-5284
+                parity = syndrome(hb, plan, tid);                                   // :5281-5284
                 if (!parity && !locked) { ret = iter + 1; locked = 1; }
                 if (!parity && !noexit) break;
             }
