@@ -133,7 +133,8 @@ int ldpcb200_destroy(ldpcb200_handle h);
 int ldpcb200_info(ldpcb200_handle h, int* N, int* R, int* E, int* device);
 
 /* Which kernel a handle runs: *fast = 0 table-driven parity kernel, >= 1 a shared-memory throughput
- * kernel (variant number + 1); launch geometry of that kernel. */
+ * kernel (bits 0-3: variant number + 1; bit 4: its check-to-variable messages live in tensor memory); launch
+ * geometry of that kernel. */
 int ldpcb200_kernel_info(ldpcb200_handle h, int* fast, int* threads, int* frames_per_cta, int* ctas_per_sm,
                          int* smem_bytes);
 

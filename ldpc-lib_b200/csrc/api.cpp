@@ -22,7 +22,7 @@ cudaError_t launch_sumprod_generic(int decoder_id, const QcDev& g, const DecPara
 }
 
 namespace ldpcb200 {
-bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant);
+bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant, bool allow_tmem);
 std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, int kind);
 bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<char>& cubin, std::string& why);
 }
@@ -352,7 +352,7 @@ int ldpcb200_info(ldpcb200_handle h, int* N, int* R, int* E, int* device)
 int ldpcb200_kernel_info(ldpcb200_handle h, int* fast, int* threads, int* frames_per_cta, int* ctas_per_sm, int* smem_bytes)
 {
     if (!h) return fail(LDPCB200_EINVAL, "null handle");
-    if (fast) *fast = h->fast.ok ? 1 + h->fast.variant : 0;
+    if (fast) *fast = h->fast.ok ? (1 + h->fast.variant) | (h->fast.tmem ? 16 : 0) : 0;
     if (threads) *threads = h->fast.ok ? h->fast.threads : h->nt;
     if (frames_per_cta) *frames_per_cta = h->fast.ok ? h->fast.frames_per_cta : 1;
     if (ctas_per_sm) *ctas_per_sm = h->fast.ok ? h->fast.ctas_per_sm : h->grid / std::max(h->num_sms, 1);
@@ -593,7 +593,8 @@ int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int
     if (!g.build(hd, b, c, Z)) return fail(LDPCB200_EINVAL, "bad base matrix");
     int zp, minb, variant;
     size_t smem;
-    if (!lms_spec_geometry(g, 233472, 232448, &zp, &minb, &smem, &variant)) return fail(LDPCB200_EUNSUPPORTED, "code does not suit the code-specialised kernel");
+    const char* no_tmem = getenv("LDPCB200_NO_TMEM");
+    if (!lms_spec_geometry(g, 233472, 232448, &zp, &minb, &smem, &variant, !(no_tmem && *no_tmem == '1'))) return fail(LDPCB200_EUNSUPPORTED, "code does not suit the code-specialised kernel");
     std::vector<char> cubin;
     std::string why;
     if (!lms_spec_compile(lms_spec_generate(g, zp, minb, variant, 0), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());

@@ -301,11 +301,33 @@ cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const F
 // launch geometry of the code-specialised kernel for g; false if the code does not suit it.
 // *variant = 0: every block column doubled in shared memory, all check state in registers (small codes);
 //            1: single copy + sign/position words in shared memory, min1/min2 in registers (large codes)
-bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant)
+//            2: doubled columns in the rotation of their last writer, c2v messages in tensor memory (lms_tmem.cuh);
+//               chosen when a frame's E*Z messages fit the 512 TMEM columns often enough to keep >= 12 warps on an SM
+size_t lms_tmem_smem_bytes(int b, int c, int Z, int maxdeg);
+size_t lms_tmem_pad_smem(size_t smem, int minb);
+
+bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant, bool allow_tmem)
 {
     if (g.E > 512 || g.Z > 1024 || g.maxdeg > MAXDEG_FAST) return false;
     *zp = (g.Z + 31) & ~31;
     const int hw = *zp / 32;
+    if (allow_tmem && g.maxdeg <= 32 && g.c * hw < 1023) {
+        int tcols = 32;
+        while (tcols < g.E * ((hw + 3) / 4)) tcols *= 2;
+        const size_t need = lms_tmem_smem_bytes(g.b, g.c, g.Z, g.maxdeg);
+        if (tcols <= 512 && need <= (size_t)smem_per_block) {
+            int m = 512 / tcols;
+            m = std::min(m, (int)((size_t)smem_per_sm / (need + 1024)));
+            m = std::min(m, 2048 / *zp);
+            m = std::min(m, 65536 / (*zp * 64));                    // at least 64 registers per thread
+            if (m >= 1 && m * hw >= 12) {
+                *minb = m;
+                *smem = std::min(lms_tmem_pad_smem(need, m), (size_t)smem_per_block);
+                *variant = 2;
+                return true;
+            }
+        }
+    }
     const size_t hb = (size_t)(g.c * hw > 4 ? g.c * hw : 4);
     for (int v = 0; v < 2; v++) {
         const size_t words = v == 0 ? 2 * (size_t)g.N + hb : (size_t)g.N + (size_t)g.R + hb;
@@ -334,7 +356,8 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
     int aot = -1;
     if (!(no_spec && *no_spec == '1')) {
         if (tmem) aot = find_lms_spec_aot(g, 3);            // messages in tensor memory (lms_tmem.cuh)
-        if (aot < 0) aot = find_lms_spec_aot(g, 0);
+        if (aot >= 0) p.tmem = 1;
+        else aot = find_lms_spec_aot(g, 0);
     }
     if (aot >= 0) {                                          // a code-specialised instance exists for this matrix
         int minb = 1;
@@ -343,16 +366,18 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
             p.ok = 1; p.variant = 1; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.spec_index = aot;
             return p;
         }
+        p.tmem = 0;
     }
     if (allow_jit && !(no_spec && *no_spec == '1')) {       // compile one for this matrix
         int zp, minb, variant;
         size_t smem;
-        if (lms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem, &variant)) {
+        if (lms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem, &variant, tmem)) {
             std::string why;
             const void* k = lms_spec_jit(g, zp, minb, variant, 0, why);
             if (k) {
                 p.ok = 1; p.variant = 2; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem;
                 p.jit_kernel = k;
+                p.tmem = variant == 2;
                 return p;
             }
             p.note = why;

@@ -82,11 +82,43 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
     put_array(o, "__constant__ int RT_RP", g.rp, g.b + 1);
     put_array(o, "__constant__ int RT_COL", g.col, g.E);
     put_array(o, "__constant__ int RT_SH", g.sh, g.E);
+    // tables of the tensor-memory kernel (lms_tmem.cuh; same as tools/gen_lms_spec.py tmem_tables): every block
+    // column is kept in the rotation of its last writer
+    std::vector<int> rot(g.c, 0), ri(g.c, 0), delta(g.E, 0), synsh(g.E, 0), lastw(g.E, 0);
+    {
+        std::vector<int> last(g.c, 0), cur, seen(g.c, 0);
+        for (int e = 0; e < g.E; e++) last[g.col[e]] = g.sh[e];
+        rot = last;
+        cur = last;
+        for (int e = 0; e < g.E; e++) {
+            delta[e] = ((g.sh[e] - cur[g.col[e]]) % g.Z + g.Z) % g.Z;
+            cur[g.col[e]] = g.sh[e];
+            synsh[e] = ((g.sh[e] - rot[g.col[e]]) % g.Z + g.Z) % g.Z;
+        }
+        for (int k = 0; k < g.c; k++) ri[k] = (g.Z - rot[k]) % g.Z;
+        for (int e = g.E - 1; e >= 0; e--)
+            if (!seen[g.col[e]]) { lastw[e] = 1; seen[g.col[e]] = 1; }
+    }
+    int tcols = 32;
+    while (tcols < g.E * ((zp / 32 + 3) / 4)) tcols *= 2;
+    put_array(o, "__constant__ int RT_ROT", rot, g.c);
+    put_array(o, "__constant__ int RT_RI", ri, g.c);
+    put_array(o, "__constant__ int RT_SYNSH", synsh, g.E);
     o << "struct Code {\n";
     o << "    static constexpr int B = " << g.b << ", C = " << g.c << ", Z = " << g.Z << ", E = " << g.E << ", ZP = " << zp << ", MINB = " << minb
       << ", MAXDEG = " << g.maxdeg << ";\n";
-    // variant 0: doubled columns, all check state in registers; 1: single copy, sign/position words in shared memory
-    o << "    static constexpr bool DOUBLED = " << (variant == 0 ? "true" : "false") << ", PS_SMEM = " << (variant == 0 ? "false" : "true") << ";\n";
+    // variant 0: doubled columns, all check state in registers; 1: single copy, sign/position words in shared memory;
+    // 2: doubled columns in the rotation of their last writer, c2v messages in tensor memory (lms_tmem.cuh)
+    o << "    static constexpr bool DOUBLED = " << (variant != 1 ? "true" : "false") << ", PS_SMEM = " << (variant != 1 ? "false" : "true") << ";\n";
+    o << "    static constexpr int TCOLS = " << tcols << ";\n";
+    put_array(o, "    static constexpr int DELTA", delta, g.E);
+    put_array(o, "    static constexpr int ROT", rot, g.c);
+    put_array(o, "    static constexpr int RI", ri, g.c);
+    put_array(o, "    static constexpr int SYNSH", synsh, g.E);
+    put_array(o, "    static constexpr bool LAST", lastw, g.E);
+    o << "    static __device__ __forceinline__ const int* rt_rot() { return RT_ROT; }\n";
+    o << "    static __device__ __forceinline__ const int* rt_ri() { return RT_RI; }\n";
+    o << "    static __device__ __forceinline__ const int* rt_synsh() { return RT_SYNSH; }\n";
     put_array(o, "    static constexpr int RP", g.rp, g.b + 1);
     put_array(o, "    static constexpr int COL", g.col, g.E);
     put_array(o, "    static constexpr int SH", g.sh, g.E);
@@ -102,7 +134,7 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
     // kind 0: LMS_DEC (layered), 1: MS_DEC fp32 (flooding), 2: IMS_DEC (flooding, fixed point)
     if (kind == 0) {
         o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io)\n";
-        o << "{ ldpcb200::LmsSpec<ldpcb200::gen_jit::Code>::kernel(io); }\n";
+        o << "{ ldpcb200::" << (variant == 2 ? "LmsTmem" : "LmsSpec") << "<ldpcb200::gen_jit::Code>::kernel(io); }\n";
     } else {
         o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)\n";
         o << "{ ldpcb200::MsSpec<ldpcb200::gen_jit::Code, " << (kind == 2 ? "true" : "false") << ">::kernel(io, sp); }\n";
