@@ -122,6 +122,25 @@ static __device__ __forceinline__ void tmem_zero_n(unsigned t)
     }
 }
 
+// two fp32 additions in one instruction (sm_100a FADD2: add.rn.f32x2 on register pairs); each half rounds exactly
+// like a scalar add.rn.f32
+static __device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1)
+{
+    unsigned long long a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+static __device__ __forceinline__ void sub_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1)
+{
+    unsigned long long a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 template <class K>
 struct LmsTmem {
     using S = LmsSpec<K>;
@@ -155,25 +174,41 @@ struct LmsTmem {
 
     // hbw = hb + warp, lane0: this lane stores the warp's packed words
     template <int J, int Q>
+    static __device__ __forceinline__ unsigned new_message(const float (&v)[K::RP[J + 1] - K::RP[J]], float c1, unsigned m1x, unsigned m2x)
+    {
+        const bool ismin = fabsf(v[Q]) == c1;
+        return (ismin ? m2x : m1x) ^ (__float_as_uint(v[Q]) & 0x80000000u);                      // decoders.cpp:5193-5198
+    }
+    template <int J, int Q>
+    static __device__ __forceinline__ void put_posterior(float* softn, unsigned* hbw, bool lane0, bool active, float nv)
+    {
+        constexpr int E0 = K::RP[J];
+        constexpr int off = K::COL[E0 + Q] * CS;
+        if (ALL_ACTIVE || active) { softn[off] = nv; softn[off + Z] = nv; }                      // lane-aligned, both copies
+        if constexpr (K::LAST[E0 + Q]) {
+            // this block row is the last one of the iteration to touch the column: its values are the
+            // iteration's posteriors, so their signs are the hard decisions the syndrome is taken of (:5281)
+            const unsigned w = __ballot_sync(0xffffffffu, (ALL_ACTIVE || active) && nv < 0.0f);
+            if (lane0) hbw[K::COL[E0 + Q] * HW] = w;
+        }
+    }
+    template <int J, int Q>
     static __device__ __forceinline__ void phase2(float* softn, unsigned* hbw, bool lane0, bool active,
                                                   const float (&v)[K::RP[J + 1] - K::RP[J]], float c1,
                                                   unsigned m1x, unsigned m2x, unsigned (&msg)[K::RP[J + 1] - K::RP[J]])
     {
-        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
-        if constexpr (Q < DEG) {
-            constexpr int off = K::COL[E0 + Q] * CS;
-            const bool ismin = fabsf(v[Q]) == c1;
-            const unsigned cv = (ismin ? m2x : m1x) ^ (__float_as_uint(v[Q]) & 0x80000000u);     // decoders.cpp:5193-5198
-            const float nv = v[Q] + __uint_as_float(cv);                                         // :5199-5204
-            msg[Q] = cv;
-            if (ALL_ACTIVE || active) { softn[off] = nv; softn[off + Z] = nv; }                  // lane-aligned, both copies
-            if constexpr (K::LAST[E0 + Q]) {
-                // this block row is the last one of the iteration to touch the column: its values are the
-                // iteration's posteriors, so their signs are the hard decisions the syndrome is taken of (:5281)
-                const unsigned w = __ballot_sync(0xffffffffu, (ALL_ACTIVE || active) && nv < 0.0f);
-                if (lane0) hbw[K::COL[E0 + Q] * HW] = w;
-            }
-            phase2<J, Q + 1>(softn, hbw, lane0, active, v, c1, m1x, m2x, msg);
+        constexpr int DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q + 1 < DEG) {
+            msg[Q] = new_message<J, Q>(v, c1, m1x, m2x);
+            msg[Q + 1] = new_message<J, Q + 1>(v, c1, m1x, m2x);
+            float n0, n1;
+            add_f32x2(n0, n1, v[Q], v[Q + 1], __uint_as_float(msg[Q]), __uint_as_float(msg[Q + 1]));    // :5199-5204
+            put_posterior<J, Q>(softn, hbw, lane0, active, n0);
+            put_posterior<J, Q + 1>(softn, hbw, lane0, active, n1);
+            phase2<J, Q + 2>(softn, hbw, lane0, active, v, c1, m1x, m2x, msg);
+        } else if constexpr (Q < DEG) {
+            msg[Q] = new_message<J, Q>(v, c1, m1x, m2x);
+            put_posterior<J, Q>(softn, hbw, lane0, active, v[Q] + __uint_as_float(msg[Q]));
         }
     }
 
@@ -235,7 +270,9 @@ struct LmsTmem {
         load_soft<J, 0>(softn, sv);
         tmem_wait_ld<DEG>(msg);
 #pragma unroll
-        for (int q = 0; q < DEG; q++) v[q] = sv[q] - __uint_as_float(msg[q]);                    // :5152-5158
+        for (int q = 0; q + 1 < DEG; q += 2)                                                     // :5152-5158, two edges per FADD2
+            sub_f32x2(v[q], v[q + 1], sv[q], sv[q + 1], __uint_as_float(msg[q]), __uint_as_float(msg[q + 1]));
+        if constexpr (DEG & 1) v[DEG - 1] = sv[DEG - 1] - __uint_as_float(msg[DEG - 1]);
         loads_done(mbar, lane0);
         const typename S::RowAcc a = two_smallest<DEG, 0, DEG>(v);
         const unsigned sacc = sign_xor<DEG, 0, DEG>(v);
@@ -464,6 +501,7 @@ struct LmsTmem {
                 if (!parity && !noexit) break;                                          // :5119
                 tmem_wait_st();                                                         // last iteration's messages are in place
                 layers<0>(softn, hbw, trow, mbar, ph, lane0, active);
+                if (locked) continue;                                                   // fixed-iteration mode after the first success: the verdict is known
                 parity = syndrome(hb, plan, tid);                                   // :5281-5284
                 if (!parity && !locked) { ret = iter + 1; locked = 1; }
                 if (!parity && !noexit) break;
