@@ -41,7 +41,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CODE, Z, SNR_DB, MAXITER, DECODER = "ref32x16_b", 256, 2.0, 10, 8      # 8 = LMS_DEC
 FRAMES_PER_GPU = 1 << 20
 METRIC, UNIT = "decoded_info_gbps_10iter", "Gbit/s"
-TRAFFIC_BYTES_PER_FRAME = (2148847000 + 19339264) / 65536        # ncu capture of the bench kernel: 33 084 B per frame
+TRAFFIC_BYTES_PER_FRAME = (2148554000 + 18556928) / 65536        # ncu capture of the bench kernel (lmst_spec_c2t): 33 067 B per frame
+# SASS instruction mix of one iteration of the bench kernel (tools/sass_mix.py on the built object; profiles/):
+# (ALU-pipe, total) instructions per edge update and lane
+SASS_MIX = {True: (6.94, 12.84, "lms_tmem (profiles/r01_lms_tmem_v5_ncu.txt, tools/sass_mix.py)"),
+            False: (13.9, 25.6, "lms_spec (profiles/r01_lms_spec_v1_ncu.txt)")}
 
 
 def load_binding():
@@ -280,6 +284,7 @@ def run_ours(args):
         sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
         edge_updates = frames * dec.E * Z * MAXITER / (kernel_ms * 1e-3)
         issue_peak = 148 * 4 * 32 * sm_hz * 1e6                      # thread-instructions / s
+        alu_ops, all_ops, mix_src = SASS_MIX[bool(info.get("tmem"))]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world, frames),
@@ -295,14 +300,15 @@ def run_ours(args):
                                "frame_failure_rate": fer_proxy},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": TRAFFIC_BYTES_PER_FRAME * frames, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame,
-                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_spec_v1 (ncu --set full, "
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_tmem_v5_ncu.txt (ncu --set full, "
                                                "65536 frames) scaled to this launch"},
                 # the binding roofline: min-sum is compare / select / logic work that issues on the
-                # ALU pipe (64 lanes / clk / SM); 13.9 ALU-pipe and 25.6 total SASS instructions per edge update
-                # (profiles/r01_lms_spec_v1_*: ncu source page and cuobjdump counts of the specialised kernel)
-                "issue": {"bound": "alu_pipe", "edge_updates_per_s": edge_updates, "alu_ops_per_edge_update": 13.9,
+                # ALU pipe (64 lanes / clk / SM); ALU-pipe and total SASS instructions per edge update of the kernel
+                # that ran (SASS_MIX above)
+                "issue": {"bound": "alu_pipe", "edge_updates_per_s": edge_updates, "alu_ops_per_edge_update": alu_ops,
+                          "instr_per_edge_update": all_ops, "source": mix_src,
                           "alu_lane_peak_per_s": 148 * 64 * sm_hz * 1e6,
-                          "frac": edge_updates * 13.9 / (148 * 64 * sm_hz * 1e6),
+                          "frac": edge_updates * alu_ops / (148 * 64 * sm_hz * 1e6),
                           "thread_instr_peak_per_s": issue_peak, "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(dec, llr, hard, iters, K)
