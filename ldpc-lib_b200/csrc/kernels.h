@@ -41,6 +41,10 @@ cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cuda
 FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit);
 cudaError_t launch_ms_fast(const FastPlan& p, const DecParams& dp, const FrameIO& io, int grid, cudaStream_t s);
 
+// TASP_DEC in double with the lambda messages in tensor memory (tasp_fast.cu); table-driven, any code that fits
+FastPlan plan_tasp_fast(const QcHost& g, int smem_per_sm, int smem_per_block);
+cudaError_t launch_tasp_fast(const FastPlan& p, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s);
+
 // ---- utilities (channel.cu)
 // packed words -> one byte per bit
 cudaError_t launch_unpack_hard(const uint32_t* words, uint8_t* bytes, int nf, int N, int nwords, cudaStream_t s);

@@ -1,0 +1,248 @@
+// TASP_DEC throughput kernel (layered sum-product in the probability domain, decoders.cpp:2584-2744), double like the
+// reference and in the reference's operation order -- the same expressions as TaspGeneric (dec_sumprod.cu), so results
+// are the parity kernel's bit for bit.  Table-driven (any code, no compilation step: this is also the kernel the
+// code-search caller gets), one frame per CTA at a time, persistent grid, lane n = check row n of every block row.
+//
+// What makes it faster than the parity kernel (which keeps everything in an L2-resident workspace and its per-row
+// arrays in local memory because the row weight is a run-time value):
+//   * lambda messages (Z[row][edge], decoders.cpp:2620-2641) in TENSOR MEMORY: two 32-bit TMEM columns per edge and
+//     lane, fetched / put back per block row with one tcgen05.ld / tcgen05.st group (run-time column address);
+//   * posteriors gamma (N doubles) in shared memory;
+//   * the block row is processed by a function templated on the row weight (switch dispatch), so rho[], the
+//     forward / backward products of map_bin and the new messages live in registers;
+//   * edge tables (bit offset, shift) in shared memory.
+// Codes whose messages do not fit the 512 TMEM columns (2 * E * ceil(threads / 128) > 512) or whose row weight exceeds
+// TASP_MAXDEG stay on the parity kernel.
+#include "dec_common.cuh"
+#include "lms_spec.cuh"
+#include "lms_tmem.cuh"
+
+namespace ldpcb200 {
+
+#define TASP_MAXDEG 20
+
+struct TaspTab {
+    int b, c, Z, N, R, E, nwords, tcols;
+};
+
+__device__ __forceinline__ double tf_mind(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double tf_maxd(double a, double b) { return a < b ? b : a; }
+
+// LLR -> P(bit = 1), decoders.cpp:2611-2618
+__device__ __forceinline__ double tf_llr_to_p1(double llr)
+{
+    double x = llr * 0.5;
+    double yv = tf_maxd(tf_mind(x, 20.0), -20.0);
+    double e0 = exp(yv);
+    double e1 = exp(-yv);
+    return e1 / (e0 + e1);
+}
+
+// map_bin, decoders.cpp:2191-2228, row weight RW >= 2 known at compile time: everything in registers
+template <int RW>
+__device__ __forceinline__ void tf_map_bin(double (&s)[RW])
+{
+    double SF[RW], SB[RW], P[RW];
+#pragma unroll
+    for (int i = 0; i < RW; i++) P[i] = 1 - 2 * s[i];
+    SF[0] = P[0];
+#pragma unroll
+    for (int i = 1; i < RW - 1; i++) SF[i] = P[i] * SF[i - 1];
+    SB[RW - 1] = P[RW - 1];
+#pragma unroll
+    for (int i = RW - 2; i > 0; i--) SB[i] = P[i] * SB[i + 1];
+    s[0] = (1 - SB[1]) / 2;
+#pragma unroll
+    for (int i = 1; i < RW - 1; i++) {
+        double Zv = SF[i - 1] * SB[i + 1];
+        s[i] = (1 - Zv) / 2;
+    }
+    s[RW - 1] = (1 - SF[RW - 2]) / 2;
+}
+
+// one block row of weight RW for check row n (clamped to Z-1 for the idle lanes of the last warp, which run the
+// warp-collective TMEM instructions but store nothing)
+template <int RW>
+__device__ __forceinline__ void tf_row(double* gam, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    const double T = 0.0001, TT = 0;                                             // decoders.cpp:2597-2598
+    unsigned lw[2 * RW];
+    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    int idx[RW];
+    double x[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];                                        // bit offset of the column | shift << 16
+        int k = n + (int)(pk >> 16);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        x[q] = gam[idx[q]];
+    }
+    tmem_wait_ld<2 * RW>(lw);
+    double rho[RW], a[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double av = __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);
+        double r = x[q] * (1.0 - av) / (av + x[q] - 2.0 * av * x[q]);           // :2686
+        if (r < TT) r = TT;                                                      // :2692-2697
+        if (r > 1 - TT) r = 1 - TT;
+        rho[q] = r; a[q] = r;
+    }
+    tf_map_bin<RW>(a);                                                           // :2699
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        double av = a[q];
+        if (av < T) av = T;                                                      // :2701-2705
+        if (av > 1.0 - T) av = 1.0 - T;
+        const double g = rho[q] * av / (1.0 - rho[q] - av + 2 * rho[q] * av);    // :2716
+        if (active) gam[idx[q]] = g;
+        lw[2 * q] = (unsigned)__double2loint(av);
+        lw[2 * q + 1] = (unsigned)__double2hiint(av);
+    }
+    tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+}
+
+template <int RW>
+__device__ __noinline__ void tf_row_call(double* gam, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    tf_row<RW>(gam, etab, e0, n, Z, active, trow);
+}
+
+__device__ __forceinline__ void tf_dispatch(int cnt, double* gam, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    switch (cnt) {
+#define TF_CASE(k) case k: tf_row_call<k>(gam, etab, e0, n, Z, active, trow); break;
+    TF_CASE(2) TF_CASE(3) TF_CASE(4) TF_CASE(5) TF_CASE(6) TF_CASE(7) TF_CASE(8) TF_CASE(9) TF_CASE(10) TF_CASE(11)
+    TF_CASE(12) TF_CASE(13) TF_CASE(14) TF_CASE(15) TF_CASE(16) TF_CASE(17) TF_CASE(18) TF_CASE(19) TF_CASE(20)
+#undef TF_CASE
+    default: break;
+    }
+}
+
+// syndrome of the decisions gamma > 0.5 (check_syndrome_thr, decoders.cpp:2274): every lane XORs its rows
+__device__ __forceinline__ int tf_syndrome(const double* gam, const unsigned* etab, const int* rpw, int b, int Z, int n, bool active)
+{
+    int bad = 0;
+    if (active) {
+        for (int j = 0; j < b; j++) {
+            int s = 0;
+            for (int e = rpw[j]; e < rpw[j + 1]; e++) {
+                const unsigned pk = etab[e];
+                int k = n + (int)(pk >> 16);
+                if (k >= Z) k -= Z;
+                s ^= (int)(gam[(int)(pk & 0xffffu) + k] > 0.5);
+            }
+            bad |= s;
+        }
+    }
+    return __syncthreads_or(bad);
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
+{
+    extern __shared__ __align__(16) double tf_smem[];
+    const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
+    double* gam = tf_smem;
+    unsigned* etab = (unsigned*)(gam + N);
+    int* rpw = (int*)(etab + E);
+    unsigned* s_t = (unsigned*)(rpw + b + 1);
+    const bool active = tid < Z;
+    const int n = active ? tid : Z - 1;
+    const bool noexit = io.flags & LDPCB200_NO_EARLY_EXIT;
+
+    for (int e = tid; e < E; e += nt) etab[e] = (unsigned)(g.col[e] * Z) | ((unsigned)g.sh[e] << 16);
+    for (int j = tid; j <= b; j += nt) rpw[j] = g.rp[j];
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(s_t)), "r"((unsigned)T.tcols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = *(volatile unsigned*)s_t;
+    // this thread's TMEM lane (bits 31:16) and first column: 2 columns per edge, 2 * E columns per group of 4 warps
+    const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * 2 * E), 0);
+
+    for (;;) {
+        const int f = next_frame(io);
+        if (f >= io.nf) break;
+        for (int i = tid; i < N; i += nt) gam[i] = tf_llr_to_p1(load_llr(io, N, f, i));          // :2611-2646
+        {   // lambda = 0.5 for every edge (:2620-2641): 0x3FE0000000000000
+            unsigned half[2] = { 0u, 0x3FE00000u };
+            for (int e = 0; e < E; e++) TmemRow<2>::st(trow + 2u * (unsigned)e, half);
+            tmem_wait_st();
+        }
+        __syncthreads();
+        int synd = tf_syndrome(gam, etab, rpw, b, Z, n, active);                                 // :2653
+        int ret = 0, locked = 0, steps = 0;
+        if (!synd) { locked = 1; ret = 0; }                                                      // :2654-2660
+        if (synd || noexit) {
+            while (steps < io.maxiter) {
+                tmem_wait_st();
+                for (int j = 0; j < b; j++) {
+                    const int e0 = rpw[j];
+                    tf_dispatch(rpw[j + 1] - e0, gam, etab, e0, n, Z, active, trow);
+                    __syncthreads();
+                }
+                // the reference re-checks after every layer (:2723); only the last verdict is used (:2733)
+                synd = tf_syndrome(gam, etab, rpw, b, Z, n, active);
+                steps++;
+                if (!synd) { if (!locked) { ret = steps; locked = 1; } if (!noexit) break; }
+            }
+        }
+        if (!locked) ret = synd ? -steps : steps;                                                // :2740-2743
+        for (int i = tid; i < N; i += nt) store_post(io, N, f, i, gam[i]);
+        emit_frame(g, io, f, ret, [&](int i) { return (int)(gam[i] > 0.5); });                   // :2738
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)T.tcols) : "memory");
+    }
+}
+
+size_t lms_tmem_pad_smem(size_t smem, int minb);
+
+FastPlan plan_tasp_fast(const QcHost& g, int smem_per_sm, int smem_per_block)
+{
+    FastPlan p;
+    const char* off = getenv("LDPCB200_NO_TASP_FAST");
+    if (off && *off == '1') return p;
+    if (g.maxdeg > TASP_MAXDEG || g.mindeg < 2 || g.N > 65535 || g.Z > 1024) return p;
+    const int zp = (g.Z + 31) & ~31;
+    int tcols = 32;
+    while (tcols < 2 * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;
+    if (tcols > 512) { p.note = "the lambda messages (2 columns per edge) do not fit tensor memory"; return p; }
+    const size_t smem = sizeof(double) * (size_t)g.N + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
+    if (smem > (size_t)smem_per_block) return p;
+    int m = 512 / tcols;
+    m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));
+    m = std::min(m, 2048 / zp);
+    m = std::min(m, 65536 / (zp * (zp <= 256 ? 255 : zp <= 512 ? 128 : 64)));     // register budget of the instance (launch_tasp_fast)
+    if (m < 1) m = 1;
+    p.ok = 1; p.variant = 0; p.tmem = 1;
+    p.threads = zp; p.frames_per_cta = 1; p.ctas_per_sm = m;
+    p.smem_bytes = std::min(lms_tmem_pad_smem(smem, m), (size_t)smem_per_block);
+    p.tab.assign(sizeof(TaspTab), 0);
+    TaspTab& T = *reinterpret_cast<TaspTab*>(p.tab.data());
+    T.b = g.b; T.c = g.c; T.Z = g.Z; T.N = g.N; T.R = g.R; T.E = g.E; T.nwords = (g.N + 31) / 32; T.tcols = tcols;
+    return p;
+}
+
+cudaError_t launch_tasp_fast(const FastPlan& p, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s)
+{
+    const TaspTab& T = *reinterpret_cast<const TaspTab*>(p.tab.data());
+    // the register budget follows the CTA size: 255 registers per thread up to 256 threads
+    void (*kern)(const TaspTab, const QcDev, const FrameIO) =
+        p.threads <= 128 ? tasp_fast_kernel<128> : p.threads <= 256 ? tasp_fast_kernel<256> : p.threads <= 512 ? tasp_fast_kernel<512> : tasp_fast_kernel<1024>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, p.threads, p.smem_bytes, s>>>(T, g, io);
+    return cudaGetLastError();
+}
+
+} // namespace ldpcb200

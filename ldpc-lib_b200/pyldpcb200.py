@@ -148,6 +148,8 @@ class Decoder:
         d["fast"] &= 15
         d["name"] = {0: "generic (table-driven, state in %s)" % ("shared memory" if d["smem_bytes"] else "an L2-resident workspace"), 1: "lms_fast_kernel (table-driven, shared memory)",
                      2: "%s (code-specialised, ahead of time)", 3: "%s (code-specialised, NVRTC)"}.get(d["fast"], "?")
+        if d["fast"] == 1 and self.decoder_id == TASP_DEC:
+            d["name"] = "tasp_fast_kernel (table-driven, double, lambda messages in tensor memory)"
         if "%s" in d["name"]:
             d["name"] %= {LMS_DEC: "lms_tmem" if d["tmem"] else "lms_spec", MS_DEC: "ms_spec<float>", IMS_DEC: "ms_spec<int>"}.get(self.decoder_id, "spec")
         return d
