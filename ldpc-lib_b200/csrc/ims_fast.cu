@@ -22,12 +22,36 @@ size_t ms_spec_smem_bytes(int c, int Z)
     return 4 * words + 8 * 512;
 }
 
-bool ms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem)
+size_t ms_tmem_smem_bytes(int c, int Z, bool is_int);
+size_t lms_tmem_pad_smem(size_t smem, int minb);
+
+// *variant = 0: check state register-compressed (ms_spec.cuh); 2: messages in tensor memory (ms_tmem.cuh)
+bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant, bool allow_tmem)
 {
-    if (g.b > 32 || g.E > 512 || g.Z > 1024 || g.maxdeg > 16) return false;
+    if (g.E > 512 || g.Z > 1024) return false;
     for (int i = 0; i < g.c; i++)
         if (g.cp[i + 1] == g.cp[i]) return false;          // pass A initialises a bit's accumulator through its first edge
     *zp = (g.Z + 31) & ~31;
+    *variant = 0;
+    if (allow_tmem && g.maxdeg <= 32) {
+        const int hw = *zp / 32;
+        int tcols = 32;
+        while (tcols < g.E * ((hw + 3) / 4)) tcols *= 2;
+        const size_t need = ms_tmem_smem_bytes(g.c, g.Z, kind == 2);
+        if (tcols <= 512 && need <= (size_t)smem_per_block) {
+            int m = 512 / tcols;
+            m = std::min(m, (int)((size_t)smem_per_sm / (need + 1024)));
+            m = std::min(m, 2048 / *zp);
+            m = std::min(m, 65536 / (*zp * 64));
+            if (m >= 1 && m * hw >= 12) {
+                *minb = m;
+                *smem = std::min(lms_tmem_pad_smem(need, m), (size_t)smem_per_block);
+                *variant = 2;
+                return true;
+            }
+        }
+    }
+    if (g.b > 32 || g.maxdeg > 16) return false;
     *smem = ms_spec_smem_bytes(g.c, g.Z);
     if (*smem > (size_t)smem_per_block) return false;
     const int regs = 3 * g.b + 72;
@@ -46,7 +70,11 @@ FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm,
     if (kind == 1 && precision != 32) return p;             // the double MS_DEC stays on the bit-exact table-driven kernel
     const char* no_spec = getenv("LDPCB200_NO_SPEC");
     if (no_spec && *no_spec == '1') return p;
-    const int aot = find_lms_spec_aot(g, kind);
+    const char* no_tmem = getenv("LDPCB200_NO_TMEM");       // 1: keep the check state register-compressed (ms_spec.cuh)
+    const bool tmem = !(no_tmem && *no_tmem == '1');
+    int aot = tmem ? find_lms_spec_aot(g, kind + 3) : -1;   // 4 / 5: messages in tensor memory (ms_tmem.cuh)
+    if (aot >= 0) p.tmem = 1;
+    else aot = find_lms_spec_aot(g, kind);
     if (aot >= 0) {
         int minb = 1;
         lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);
@@ -55,14 +83,16 @@ FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm,
             return p;
         }
     }
+    p.tmem = 0;
     if (allow_jit) {
-        int zp, minb;
+        int zp, minb, variant;
         size_t smem;
-        if (ms_spec_geometry(g, smem_per_sm, smem_per_block, &zp, &minb, &smem)) {
+        if (ms_spec_geometry(g, kind, smem_per_sm, smem_per_block, &zp, &minb, &smem, &variant, tmem)) {
             std::string why;
-            const void* k = lms_spec_jit(g, zp, minb, 0, kind, why);
+            const void* k = lms_spec_jit(g, zp, minb, variant, kind, why);
             if (k) {
                 p.ok = 1; p.variant = 2; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem; p.jit_kernel = k;
+                p.tmem = variant == 2;
                 return p;
             }
             p.note = why;

@@ -137,7 +137,7 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
         o << "{ ldpcb200::" << (variant == 2 ? "LmsTmem" : "LmsSpec") << "<ldpcb200::gen_jit::Code>::kernel(io); }\n";
     } else {
         o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)\n";
-        o << "{ ldpcb200::MsSpec<ldpcb200::gen_jit::Code, " << (kind == 2 ? "true" : "false") << ">::kernel(io, sp); }\n";
+        o << "{ ldpcb200::" << (variant == 2 ? "MsTmem" : "MsSpec") << "<ldpcb200::gen_jit::Code, " << (kind == 2 ? "true" : "false") << ">::kernel(io, sp); }\n";
     }
     return o.str();
 }

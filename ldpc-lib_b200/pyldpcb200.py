@@ -151,7 +151,7 @@ class Decoder:
         if d["fast"] == 1 and self.decoder_id == TASP_DEC:
             d["name"] = "tasp_fast_kernel (table-driven, double, lambda messages in tensor memory)"
         if "%s" in d["name"]:
-            d["name"] %= {LMS_DEC: "lms_tmem" if d["tmem"] else "lms_spec", MS_DEC: "ms_spec<float>", IMS_DEC: "ms_spec<int>"}.get(self.decoder_id, "spec")
+            d["name"] %= {LMS_DEC: "lms_tmem" if d["tmem"] else "lms_spec", MS_DEC: "ms_tmem<float>" if d["tmem"] else "ms_spec<float>", IMS_DEC: "ms_tmem<int>" if d["tmem"] else "ms_spec<int>"}.get(self.decoder_id, "spec")
         return d
 
     def post_dtype(self):
