@@ -309,8 +309,8 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
         CU(cudaMemset(h->bpsynd.p, 0, (size_t)h->g.R + 16));
         if (p.use_fast) {
             if (decoder_id == LDPCB200_LMS_DEC) h->fast = plan_lms_fast(h->g, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
-            else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ms_fast(h->g, 2, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
-            else if (decoder_id == LDPCB200_MS_DEC) h->fast = plan_ms_fast(h->g, 1, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
+            else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ms_fast(h->g, 2, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
+            else if (decoder_id == LDPCB200_MS_DEC) h->fast = plan_ms_fast(h->g, 1, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
             else if (decoder_id == LDPCB200_TASP_DEC) h->fast = plan_tasp_fast(h->g, h->smem_per_sm, h->smem_per_block);
         }
         return 0;

@@ -33,7 +33,7 @@ bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_b
         if (g.cp[i + 1] == g.cp[i]) return false;          // pass A initialises a bit's accumulator through its first edge
     *zp = (g.Z + 31) & ~31;
     *variant = 0;
-    if (allow_tmem && g.maxdeg <= 32) {
+    if (allow_tmem && g.maxdeg <= 32) {                     // (plan_ms_fast clears allow_tmem when IMS_DEC's integers would not be exact in fp32)
         const int hw = *zp / 32;
         int tcols = 32;
         while (tcols < g.E * ((hw + 3) / 4)) tcols *= 2;
@@ -64,14 +64,19 @@ bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_b
 }
 
 // kind: 1 = MS_DEC (precision 32 only), 2 = IMS_DEC
-FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit)
+FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit, const DecParams& dp)
 {
     FastPlan p;
     if (kind == 1 && precision != 32) return p;             // the double MS_DEC stays on the bit-exact table-driven kernel
     const char* no_spec = getenv("LDPCB200_NO_SPEC");
     if (no_spec && *no_spec == '1') return p;
     const char* no_tmem = getenv("LDPCB200_NO_TMEM");       // 1: keep the check state register-compressed (ms_spec.cuh)
-    const bool tmem = !(no_tmem && *no_tmem == '1');
+    bool tmem = !(no_tmem && *no_tmem == '1');
+    if (kind == 2) {
+        // ms_tmem.cuh carries IMS_DEC's integers as floats: exact while max_data * ialpha < 2^24 (always, for sane alpha)
+        const double ialpha = (double)(int)(dp.alpha * 16), max_data = (double)((1L << (dp.dbits - 1)) - 1);
+        if (!(dp.alpha >= 0) || ialpha * max_data >= 16777216.0) tmem = false;
+    }
     int aot = tmem ? find_lms_spec_aot(g, kind + 3) : -1;   // 4 / 5: messages in tensor memory (ms_tmem.cuh)
     if (aot >= 0) p.tmem = 1;
     else aot = find_lms_spec_aot(g, kind);

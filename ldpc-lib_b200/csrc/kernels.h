@@ -38,7 +38,7 @@ struct FastPlan {
 FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem_per_block, int allow_jit);
 cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cudaStream_t s);
 // flooding min-sum pair (ims_fast.cu -> ms_spec.cuh): kind 1 = MS_DEC fp32, 2 = IMS_DEC
-FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit);
+FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit, const DecParams& dp);
 cudaError_t launch_ms_fast(const FastPlan& p, const DecParams& dp, const FrameIO& io, int grid, cudaStream_t s);
 
 // TASP_DEC in double with the lambda messages in tensor memory (tasp_fast.cu); table-driven, any code that fits

@@ -14,6 +14,10 @@
 //     stay in bit order (the IMS quantiser sums their squares sequentially), the column rotation is applied here;
 //   * pass C per check row, no barriers: v2c = soft - alpha * old (MS) / soft - old (IMS), syndrome of this pass's
 //     decisions, two smallest |v2c|, new messages.
+// IMS_DEC's fixed-point values are small integers (|x| <= 2^dbits, products with ialpha < 2^24), which fp32 represents
+// and adds / subtracts / compares / scales by ialpha/16 EXACTLY; the kernel therefore carries them as integer-valued
+// floats and shares MS_DEC's instruction stream (FADD, FMNMX for the saturation, sign-bit logic) -- the results are the
+// reference's integers bit for bit (the host checks max_data * ialpha < 2^24 before choosing this kernel).
 // This header must stay free of #include (NVRTC), and follows lms_tmem.cuh in the translation unit.
 #pragma once
 
@@ -69,13 +73,14 @@ struct MsTmem {
             constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
             unsigned msg[DEG];
             float acc[DEG];
+            const float mx = (float)sp.max_data;
             tmem_ld_n<DEG>(trow + E0, msg);
             accA_load<J, 0>(softn, acc);
             tmem_wait_ld<DEG>(msg);
 #pragma unroll
             for (int q = 0; q < DEG; q++) {
-                if constexpr (IS_INT) acc[q] = __int_as_float(sat(__float_as_int(acc[q]) + (int)msg[q], sp.max_data));   // :5567-5568
-                else acc[q] = __fadd_rn(acc[q], __uint_as_float(msg[q]));                                              // :4658
+                acc[q] = __fadd_rn(acc[q], __uint_as_float(msg[q]));                             // :4658 / :5567
+                if constexpr (IS_INT) acc[q] = fminf(fmaxf(acc[q], -mx), mx);                    // :5568 saturate after every add
             }
             T::loads_done(mbar, lane0);
             if constexpr (B % 2 == 0) T::wait_loads(mbar, J & 1);
@@ -97,8 +102,8 @@ struct MsTmem {
             const float yv = y[COL * Z + k];
             const float a = softn[COL * CS];
             float s;
-            if constexpr (IS_INT) s = __int_as_float(sat(__float_as_int(yv) + __float_as_int(a), sp.max_data));
-            else s = __fadd_rn(yv, __fmul_rn(a, sp.alpha));
+            if constexpr (IS_INT) s = fminf(fmaxf(__fadd_rn(yv, a), -(float)sp.max_data), (float)sp.max_data);   // :5599-5601
+            else s = __fadd_rn(yv, __fmul_rn(a, sp.alpha));                                      // :4682
             softn[COL * CS] = s; softn[COL * CS + Z] = s;
             passB<COL + 1>(softn, y, tid, sp);
         }
@@ -125,46 +130,29 @@ struct MsTmem {
             tmem_ld_n<DEG>(trow + E0, msg);
             softC_load<J, 0>(softn, rs);
             tmem_wait_ld<DEG>(msg);
-            unsigned synd = 0, sacc = 0;
+            unsigned synd = 0;
+#pragma unroll
+            for (int q = 0; q < DEG; q++) {
+                synd ^= __float_as_uint(rs[q]);                                                  // :4711 / :5631 (sign bit = rs < 0)
+                if constexpr (IS_INT) v[q] = __fsub_rn(rs[q], __uint_as_float(msg[q]));          // :5646, the message is already scaled (:5640)
+                else v[q] = __fsub_rn(rs[q], __fmul_rn(__uint_as_float(msg[q]), sp.alpha));      // :4714-4722
+            }
+            const typename S::RowAcc a = T::template two_smallest<DEG, 0, DEG>(v);               // :4732-4746 / :5656-5666
+            const unsigned rsg = T::template sign_xor<DEG, 0, DEG>(v) & 0x80000000u;
+            float n1, n2;
             if constexpr (IS_INT) {
-                int c1 = 0x7fffffff, c2 = 0x7fffffff;
-#pragma unroll
-                for (int q = 0; q < DEG; q++) {
-                    const int r = __float_as_int(rs[q]);
-                    synd ^= (unsigned)r;                                                         // :5631 (sign bit = rs < 0)
-                    const int x = r - (int)msg[q];                                               // :5646, the message is already scaled (:5640)
-                    v[q] = __int_as_float(x);
-                    sacc ^= (unsigned)x;
-                    const int a = x < 0 ? -x : x;
-                    c2 = min(c2, max(c1, a));                                                    // :5656-5666
-                    c1 = min(c1, a);
-                }
-                const int t1 = (min(c1, sp.max_data) * sp.ialpha) >> 4;                          // :5653, :5554
-                const int t2 = (min(c2, sp.max_data) * sp.ialpha) >> 4;
-#pragma unroll
-                for (int q = 0; q < DEG; q++) {
-                    const int x = __float_as_int(v[q]);
-                    const bool ismin = (x < 0 ? -x : x) == c1;
-                    const int t = ismin ? t2 : t1;                                               // :5551
-                    const bool neg = (int)((unsigned)x ^ sacc) < 0;                              // c2v sign = sign(v2c) ^ row sign
-                    msg[q] = (unsigned)(neg ? -t : t);
-                }
+                const float mx = (float)sp.max_data, scale = (float)sp.ialpha * 0.0625f;
+                n1 = floorf(__fmul_rn(fminf(a.c1, mx), scale));                                  // :5653, (min * ialpha) >> 4 :5554
+                n2 = floorf(__fmul_rn(fminf(a.c2, mx), scale));
             } else {
+                n1 = fminf(a.c1, 32767.0f);                                                      // :4730, init :4692-4696
+                n2 = fminf(a.c2, 32767.0f);
+            }
+            const unsigned m1x = __float_as_uint(n1) ^ rsg, m2x = __float_as_uint(n2) ^ rsg;
 #pragma unroll
-                for (int q = 0; q < DEG; q++) {
-                    synd ^= __float_as_uint(rs[q]);                                              // :4711
-                    v[q] = __fsub_rn(rs[q], __fmul_rn(__uint_as_float(msg[q]), sp.alpha));       // :4714-4722
-                }
-                const typename S::RowAcc a = T::template two_smallest<DEG, 0, DEG>(v);
-                sacc = T::template sign_xor<DEG, 0, DEG>(v);
-                const unsigned rsg = sacc & 0x80000000u;
-                const unsigned m1x = __float_as_uint(fminf(a.c1, 32767.0f)) ^ rsg;               // :4730, init :4692-4696
-                const unsigned m2x = __float_as_uint(fminf(a.c2, 32767.0f)) ^ rsg;
-#pragma unroll
-                for (int q = 0; q < DEG; q++) {
-                    const bool ismin = fabsf(v[q]) == a.c1;
-                    msg[q] = (ismin ? m2x : m1x) ^ (__float_as_uint(v[q]) & 0x80000000u);
-                }
+            for (int q = 0; q < DEG; q++) {
+                const bool ismin = fabsf(v[q]) == a.c1;
+                msg[q] = (ismin ? m2x : m1x) ^ (__float_as_uint(v[q]) & 0x80000000u);            // c2v sign = sign(v2c) ^ row sign
             }
             bad |= synd;
             tmem_st_n<DEG>(trow + E0, msg);                                                      // :4753 / :5675
@@ -266,7 +254,7 @@ struct MsTmem {
                     if (val > sp.thr) val = sp.thr;
                     const int ival = (short)floor(val * sp.max_quant / sp.thr + 0.5);
                     const int q = sign ? -ival : ival;
-                    y[i] = __int_as_float(q);
+                    y[i] = (float)q;
                     if (io.aux) io.aux[(size_t)f * N + i] = (short)q;
                 }
                 __syncthreads();
@@ -300,7 +288,7 @@ struct MsTmem {
                     if (ALL_ACTIVE || active) {
                         const size_t k = (size_t)f * N + col * Z + tid;
                         const float s = soft2[col * CS + tid + K::rt_ri()[col]];
-                        if constexpr (IS_INT) ((short*)io.post)[k] = (short)__float_as_int(s);
+                        if constexpr (IS_INT) ((short*)io.post)[k] = (short)(int)s;
                         else if (io.post_dtype == 1) ((float*)io.post)[k] = s;
                         else ((double*)io.post)[k] = (double)s;
                     }
@@ -314,7 +302,7 @@ struct MsTmem {
                     if (i < N) {
                         const int col = i / Z, k = i - col * Z;
                         const float s = soft2[col * CS + k + K::rt_ri()[col]];
-                        bit = (int)(__float_as_uint(s) >> 31) & (IS_INT ? 1 : (s < 0.0f));
+                        bit = s < 0.0f;
                     }
                     const unsigned w = __ballot_sync(0xffffffffu, bit);
                     if (lane == 0) {
