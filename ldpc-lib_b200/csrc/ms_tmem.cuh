@@ -41,8 +41,6 @@ struct MsTmem {
     static constexpr int SQ_OFF = (MISC_OFF + 4 + 1) & ~1;
     static constexpr int SMEM_WORDS = SQ_OFF + (IS_INT ? 1024 : 0);
 
-    static __device__ __forceinline__ int sat(int x, int mx) { return x > mx ? mx : (x < -mx ? -mx : x); }   // limit_val :4308
-
     // ---- pass A, block row J: acc[bit] += message, in ascending block-row order per bit
     template <int J, int Q>
     static __device__ __forceinline__ void accA_load(const float* softn, float (&acc)[K::RP[J + 1] - K::RP[J]])

@@ -1,0 +1,70 @@
+"""The tensor-memory kernels (lms_tmem.cuh, ms_tmem.cuh, tasp_fast.cu) against their register-compressed / table-driven
+twins on identical buffers: same decisions, iteration counts and posteriors bit for bit, for the ahead-of-time and the
+run-time compiled instances, full and ragged lane counts; and a long run that would expose a race between the lanes
+of a layer (the write-after-read hazard the split mbarrier closes)."""
+import numpy as np
+import pytest
+
+from codes import load_code, awgn_llr
+
+pytestmark = pytest.mark.gpu
+
+
+def _llr(code, Z, snr, nf, seed):
+    hd, _ = load_code(code)
+    b, c = hd.shape
+    return hd, awgn_llr(np.random.default_rng(seed), nf, c * Z, b, c, snr).astype(np.float32)
+
+
+@pytest.mark.parametrize("dec,prec", [("LMS", 32), ("MS", 32), ("IMS", 64)])
+@pytest.mark.parametrize("code,Z,snr", [("ref32x16_b", 256, 2.5), ("ref32x16_b", 126, 2.5), ("c4_wifi_12x24", 81, 2.0),
+                                         ("c4_wifi_12x24", 384, 2.0), ("ref32x16_a", 126, 2.5)])
+def test_tmem_kernel_equals_register_kernel(ldpc, po, monkeypatch, dec, prec, code, Z, snr):
+    hd, llr = _llr(code, Z, snr, 300, 31)
+    did = getattr(po, dec)
+    monkeypatch.delenv("LDPCB200_NO_TMEM", raising=False)
+    with ldpc.Decoder(hd, Z, did, precision=prec, use_fast=2) as d:
+        info = d.kernel_info()
+        assert info["tmem"] and info["fast"] >= 2, info
+        a = d.decode(llr, 12, want_post=True, want_aux=(dec == "IMS"))
+        fixed = d.decode(llr, 12, no_early_exit=True)
+    monkeypatch.setenv("LDPCB200_NO_TMEM", "1")
+    with ldpc.Decoder(hd, Z, did, precision=prec, use_fast=2) as d:
+        info = d.kernel_info()
+        assert not info["tmem"] and info["fast"] >= 2, info
+        b = d.decode(llr, 12, want_post=True, want_aux=(dec == "IMS"))
+    assert np.array_equal(a["iters"], b["iters"])
+    assert np.array_equal(a["hard"], b["hard"])
+    assert np.array_equal(a["post"], b["post"])
+    if dec == "IMS":
+        assert np.array_equal(a["aux"], b["aux"])
+    assert np.array_equal(fixed["iters"], a["iters"])                    # fixed-iteration mode reports the first success
+
+
+def test_tasp_fast_equals_parity_kernel(ldpc, po, monkeypatch):
+    for code, Z, snr in [("ref32x16_b", 126, 2.0), ("c4_wifi_12x24", 81, 1.5), ("ref32x16_b", 256, 2.0)]:
+        hd, llr = _llr(code, Z, snr, 200, 33)
+        llr = llr.astype(np.float64)
+        monkeypatch.delenv("LDPCB200_NO_TASP_FAST", raising=False)
+        with ldpc.Decoder(hd, Z, po.TASP) as d:
+            assert d.kernel_info()["tmem"], d.kernel_info()
+            a = d.decode(llr, 30, want_post=True)
+        monkeypatch.setenv("LDPCB200_NO_TASP_FAST", "1")
+        with ldpc.Decoder(hd, Z, po.TASP) as d:
+            assert d.kernel_info()["fast"] == 0
+            b = d.decode(llr, 30, want_post=True)
+        assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["hard"], b["hard"])
+        assert np.array_equal(a["post"], b["post"])                       # same expressions, same order: bitwise
+        want = po.orc_decode(po.TASP, hd, Z, llr[:60], 30)
+        assert np.array_equal(a["iters"][:60], want["iters"]) and np.array_equal(a["hard"][:60], want["hard"])
+
+
+def test_tmem_lms_long_run_against_oracle(ldpc, po):
+    """6 000 frames at the waterfall: any ordering bug between the lanes of a layer shows up as a handful of frames."""
+    hd, llr = _llr("ref32x16_b", 256, 2.2, 6000, 35)
+    with ldpc.Decoder(hd, 256, po.LMS, precision=32) as d:
+        assert d.kernel_info()["tmem"]
+        got = d.decode(llr, 10, packed=True)
+    want = po.orc_decode(po.LMS, hd, 256, llr, 10, dtype=np.float32)
+    assert np.array_equal(got["iters"], want["iters"])
+    assert np.array_equal(got["hard"], np.packbits(want["hard"], axis=1, bitorder="little").view(np.uint32)[:, :got["hard"].shape[1]])
