@@ -164,9 +164,9 @@ struct AspGeneric {
                         q01 = q01 * (1 - d0);
                         p1 = q10 * d0;
                         p0 = q00 * (1 - d0);
-                        so[v] = p1 / (p0 + p1);
-                        msg[ma] = q10 / (q10 + q00);
-                        msg[mb] = q11 / (q11 + q01);
+                        so[v] = div_normal(p1, p0 + p1);                          // operands are normal numbers: dec_common.cuh
+                        msg[ma] = div_normal(q10, q10 + q00);
+                        msg[mb] = div_normal(q11, q11 + q01);
                     }
                     __syncthreads();
                 } else {
@@ -180,16 +180,16 @@ struct AspGeneric {
                             P1 *= d;
                             P0 *= 1 - d;
                         }
-                        so[v] = P1 / (P0 + P1);
+                        so[v] = div_normal(P1, P0 + P1);
                     }
                     __syncthreads();
                     for (int x = tid; x < g.E * Z; x += nt) {                    // local data updating, :2525-2558
                         const int e = x / Z, n = x - e * Z;
                         double s1 = so[g.col[e] * Z + wrapz(n + g.sh[e], Z)];
                         double sos = msg[x];
-                        double p1 = s1 / sos;
-                        double p0 = (1 - s1) / (1 - sos);
-                        double d = p1 / (p1 + p0);
+                        double p1 = div_normal(s1, sos);
+                        double p0 = div_normal(1 - s1, 1 - sos);
+                        double d = div_normal(p1, p1 + p0);
                         msg[x] = maxd(mind(d, 1.0 - 0.000001), 0.000001);        // SP_DEC_MIN/MAX_VAL, :96-97
                     }
                     __syncthreads();

@@ -38,28 +38,6 @@ __device__ __forceinline__ double tf_llr_to_p1(double llr)
     return e1 / (e0 + e1);
 }
 
-// n / d, correctly rounded (IEEE round-to-nearest, the reference's x86 divsd), WITHOUT the range-check branch and the
-// slow-path call that the compiler attaches to every double division: the instruction sequence of nvcc's own fast path
-// (MUFU.RCP64H seed, two Newton steps on the reciprocal, one residual correction of the quotient), which is exact
-// whenever both operands and the quotient are normal numbers far from the exponent limits.  Here d is a sum of
-// products of probabilities clamped to [1e-4, 1 - 1e-4] (so 1e-8 < d <= 1) and 0 <= n <= 1 with n >= e^-40 or n = 0.
-// Straight-line code lets the scheduler interleave the 2 * RW independent divisions of a block row; with the branch
-// each division was its own basic block and the kernel sat in fixed-latency stalls.  tests/test_gpu_tmem.py checks
-// the kernel's posteriors bitwise against the parity kernel, which divides with operator /.
-__device__ __forceinline__ double tf_div(double n, double d)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = __fma_rn(-d, y, 1.0);
-    e = __fma_rn(e, e, e);
-    y = __fma_rn(y, e, y);
-    e = __fma_rn(-d, y, 1.0);
-    y = __fma_rn(y, e, y);
-    const double q = __dmul_rn(n, y);
-    const double r = __fma_rn(-d, q, n);
-    return __fma_rn(y, r, q);
-}
-
 // map_bin, decoders.cpp:2191-2228, row weight RW >= 2 known at compile time: everything in registers
 template <int RW>
 __device__ __forceinline__ void tf_map_bin(double (&s)[RW])
@@ -105,7 +83,7 @@ __device__ __forceinline__ void tf_row(double* gam, const unsigned* etab, int e0
 #pragma unroll
     for (int q = 0; q < RW; q++) {
         const double av = __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);
-        double r = tf_div(x[q] * (1.0 - av), av + x[q] - 2.0 * av * x[q]);       // :2686
+        double r = div_normal(x[q] * (1.0 - av), av + x[q] - 2.0 * av * x[q]);       // :2686
         if (r < TT) r = TT;                                                      // :2692-2697
         if (r > 1 - TT) r = 1 - TT;
         rho[q] = r; a[q] = r;
@@ -116,7 +94,7 @@ __device__ __forceinline__ void tf_row(double* gam, const unsigned* etab, int e0
         double av = a[q];
         if (av < T) av = T;                                                      // :2701-2705
         if (av > 1.0 - T) av = 1.0 - T;
-        const double g = tf_div(rho[q] * av, 1.0 - rho[q] - av + 2 * rho[q] * av);   // :2716
+        const double g = div_normal(rho[q] * av, 1.0 - rho[q] - av + 2 * rho[q] * av);   // :2716
         if (active) gam[idx[q]] = g;
         lw[2 * q] = (unsigned)__double2loint(av);
         lw[2 * q + 1] = (unsigned)__double2hiint(av);
