@@ -41,9 +41,9 @@ cudaError_t launch_lms_fast(const FastPlan& p, const FrameIO& io, int grid, cuda
 FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit, const DecParams& dp);
 cudaError_t launch_ms_fast(const FastPlan& p, const DecParams& dp, const FrameIO& io, int grid, cudaStream_t s);
 
-// TASP_DEC in double with the lambda messages in tensor memory (tasp_fast.cu); table-driven, any code that fits
-FastPlan plan_tasp_fast(const QcHost& g, int smem_per_sm, int smem_per_block);
-cudaError_t launch_tasp_fast(const FastPlan& p, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s);
+// TASP_DEC / ASP_DEC in double with the messages in tensor memory (tasp_fast.cu); table-driven, any code that fits
+FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block);
+cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s);
 
 // ---- utilities (channel.cu)
 // packed words -> one byte per bit

@@ -128,7 +128,7 @@ __device__ __forceinline__ int tf_syndrome(const double* gam, const unsigned* et
             int s = 0;
             for (int e = rpw[j]; e < rpw[j + 1]; e++) {
                 const unsigned pk = etab[e];
-                int k = n + (int)(pk >> 16);
+                int k = n + (int)((pk >> 16) & 0x7fffu);
                 if (k >= Z) k -= Z;
                 s ^= (int)(gam[(int)(pk & 0xffffu) + k] > 0.5);
             }
@@ -205,19 +205,188 @@ __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// ASP_DEC (flooding sum-product in the probability domain, sum_prod_gf2_decod_qc_lm, decoders.cpp:2324-2581; the general
+// path -- codes whose columns all have weight 2 take the reference's shortcut :2432-2482 and stay on the parity kernel).
+// Same recipe: messages (two TMEM words per edge and lane), block rows templated on their weight, div_normal.  An
+// iteration is three sweeps:
+//   R  block row by block row (barrier in between): map_bin on the row's messages (:2406-2428), then the row multiplies
+//      its new messages into the per-bit products P1 *= d, P0 *= 1 - d (:2489-2520).  The reference multiplies a bit's
+//      messages in ascending block-row order starting from the prior; lanes of one block row touch disjoint bits and a
+//      bit gets at most one message per block row, so the order is the reference's (the first block row of a column
+//      starts from the prior instead of reading the product);
+//   V  per bit: so = P1 / (P0 + P1) (:2522);
+//   E  per check row, no barriers: msg = clamp(p1 / (p1 + p0)), p1 = so / d, p0 = (1 - so) / (1 - d) (:2525-2558).
+template <int RW>
+__device__ __noinline__ void af_rowR(double* A, double* Bv, const double* prior, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    unsigned lw[2 * RW];
+    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    int idx[RW];
+    double P1[RW], P0[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];                                        // bit offset | shift << 16 | first-of-column << 31
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        if (pk >> 31) { P1[q] = prior[idx[q]]; P0[q] = 1 - P1[q]; }              // :2489-2490
+        else { P1[q] = A[idx[q]]; P0[q] = Bv[idx[q]]; }
+    }
+    tmem_wait_ld<2 * RW>(lw);
+    double a[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) a[q] = __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);
+    tf_map_bin<RW>(a);                                                           // :2406-2428
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        if (active) { A[idx[q]] = P1[q] * a[q]; Bv[idx[q]] = P0[q] * (1 - a[q]); }   // :2496-2497
+        lw[2 * q] = (unsigned)__double2loint(a[q]);
+        lw[2 * q + 1] = (unsigned)__double2hiint(a[q]);
+    }
+    tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+}
+
+template <int RW>
+__device__ __noinline__ void af_rowE(const double* A, const unsigned* etab, int e0, int n, int Z, unsigned trow)
+{
+    unsigned lw[2 * RW];
+    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    double s1[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        s1[q] = A[(int)(pk & 0xffffu) + k];
+    }
+    tmem_wait_ld<2 * RW>(lw);
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double sos = __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);
+        const double p1 = div_normal(s1[q], sos);                                // :2537-2550
+        const double p0 = div_normal(1 - s1[q], 1 - sos);
+        double d = div_normal(p1, p1 + p0);
+        d = tf_maxd(tf_mind(d, 1.0 - 0.000001), 0.000001);                       // SP_DEC_MIN/MAX_VAL, :96-97
+        lw[2 * q] = (unsigned)__double2loint(d);
+        lw[2 * q + 1] = (unsigned)__double2hiint(d);
+    }
+    tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+}
+
+#define AF_CASES(CALL) \
+    CALL(2) CALL(3) CALL(4) CALL(5) CALL(6) CALL(7) CALL(8) CALL(9) CALL(10) CALL(11) CALL(12) CALL(13) CALL(14) CALL(15) CALL(16) \
+    CALL(17) CALL(18) CALL(19) CALL(20)
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) asp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
+{
+    extern __shared__ __align__(16) double tf_smem[];
+    const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
+    double* A = tf_smem;                 // per-bit product P1, then the posterior so
+    double* Bv = A + N;                  // per-bit product P0
+    double* prior = Bv + N;              // p = P(bit = 1 | channel)
+    unsigned* etab = (unsigned*)(prior + N);
+    int* rpw = (int*)(etab + E);
+    unsigned* s_t = (unsigned*)(rpw + b + 1);
+    const bool active = tid < Z;
+    const int n = active ? tid : Z - 1;
+    const bool noexit = io.flags & LDPCB200_NO_EARLY_EXIT;
+
+    for (int e = tid; e < E; e += nt) {
+        const int c = g.col[e];
+        etab[e] = (unsigned)(c * Z) | ((unsigned)g.sh[e] << 16) | (g.cedge[g.cp[c]] == e ? 0x80000000u : 0u);
+    }
+    for (int j = tid; j <= b; j += nt) rpw[j] = g.rp[j];
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(s_t)), "r"((unsigned)T.tcols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = *(volatile unsigned*)s_t;
+    const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * 2 * E), 0);
+
+    for (;;) {
+        const int f = next_frame(io);
+        if (f >= io.nf) break;
+        for (int i = tid; i < N; i += nt) { const double pv = tf_llr_to_p1(load_llr(io, N, f, i)); prior[i] = pv; A[i] = pv; }   // :2351-2358
+        __syncthreads();
+        for (int e = 0; e < E; e++) {                                                            // msg = prior of the edge's bit, :2361-2378
+            const unsigned pk = etab[e];
+            int k = n + (int)((pk >> 16) & 0x7fffu);
+            if (k >= Z) k -= Z;
+            const double pv = prior[(int)(pk & 0xffffu) + k];
+            unsigned w[2] = { (unsigned)__double2loint(pv), (unsigned)__double2hiint(pv) };
+            TmemRow<2>::st(trow + 2u * (unsigned)e, w);
+        }
+        tmem_wait_st();
+        int synd = tf_syndrome(A, etab, rpw, b, Z, n, active);                                   // :2392 (bit 31 of etab is masked there)
+        int ret = 0, locked = 0, steps = 0;
+        if (!synd) { locked = 1; ret = 0; }
+        if (synd || noexit) {
+            while (steps < io.maxiter) {
+                for (int j = 0; j < b; j++) {                                                    // sweep R
+                    const int e0 = rpw[j];
+                    switch (rpw[j + 1] - e0) {
+#define AF_R(k) case k: af_rowR<k>(A, Bv, prior, etab, e0, n, Z, active, trow); break;
+                    AF_CASES(AF_R)
+#undef AF_R
+                    default: break;
+                    }
+                    __syncthreads();
+                }
+                for (int i = tid; i < N; i += nt) A[i] = div_normal(A[i], Bv[i] + A[i]);         // sweep V, :2522
+                __syncthreads();
+                tmem_wait_st();
+                for (int j = 0; j < b; j++) {                                                    // sweep E
+                    const int e0 = rpw[j];
+                    switch (rpw[j + 1] - e0) {
+#define AF_E(k) case k: af_rowE<k>(A, etab, e0, n, Z, trow); break;
+                    AF_CASES(AF_E)
+#undef AF_E
+                    default: break;
+                    }
+                }
+                tmem_wait_st();
+                synd = tf_syndrome(A, etab, rpw, b, Z, n, active);                               // :2566
+                steps++;
+                if (!synd) { if (!locked) { ret = steps; locked = 1; } if (!noexit) break; }
+            }
+        }
+        if (!locked) ret = -steps;
+        for (int i = tid; i < N; i += nt) store_post(io, N, f, i, A[i]);
+        emit_frame(g, io, f, ret, [&](int i) { return (int)(A[i] > 0.5); });                     // make_output :2308
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)T.tcols) : "memory");
+    }
+}
+
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
-FastPlan plan_tasp_fast(const QcHost& g, int smem_per_sm, int smem_per_block)
+// decoder_id: LDPCB200_TASP_DEC or LDPCB200_ASP_DEC
+FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block)
 {
     FastPlan p;
     const char* off = getenv("LDPCB200_NO_TASP_FAST");
     if (off && *off == '1') return p;
     if (g.maxdeg > TASP_MAXDEG || g.mindeg < 2 || g.N > 65535 || g.Z > 1024) return p;
+    const bool asp = decoder_id == LDPCB200_ASP_DEC;
+    if (asp && g.all_cw_2) { p.note = "all columns have weight 2: the reference's shortcut arithmetic stays on the parity kernel"; return p; }
+    for (int i = 0; asp && i < g.c; i++)
+        if (g.cp[i + 1] == g.cp[i]) return p;                           // sweep R starts a bit's product at its first edge
     const int zp = (g.Z + 31) & ~31;
     int tcols = 32;
     while (tcols < 2 * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;
     if (tcols > 512) { p.note = "the lambda messages (2 columns per edge) do not fit tensor memory"; return p; }
-    const size_t smem = sizeof(double) * (size_t)g.N + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
+    const size_t smem = sizeof(double) * (size_t)g.N * (asp ? 3 : 1) + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
     if (smem > (size_t)smem_per_block) return p;
     int m = 512 / tcols;
     m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));
@@ -233,12 +402,15 @@ FastPlan plan_tasp_fast(const QcHost& g, int smem_per_sm, int smem_per_block)
     return p;
 }
 
-cudaError_t launch_tasp_fast(const FastPlan& p, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s)
+cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s)
 {
     const TaspTab& T = *reinterpret_cast<const TaspTab*>(p.tab.data());
     // the register budget follows the CTA size: 255 registers per thread up to 256 threads
-    void (*kern)(const TaspTab, const QcDev, const FrameIO) =
-        p.threads <= 128 ? tasp_fast_kernel<128> : p.threads <= 256 ? tasp_fast_kernel<256> : p.threads <= 512 ? tasp_fast_kernel<512> : tasp_fast_kernel<1024>;
+    void (*kern)(const TaspTab, const QcDev, const FrameIO);
+    if (decoder_id == LDPCB200_ASP_DEC)
+        kern = p.threads <= 128 ? asp_fast_kernel<128> : p.threads <= 256 ? asp_fast_kernel<256> : p.threads <= 512 ? asp_fast_kernel<512> : asp_fast_kernel<1024>;
+    else
+        kern = p.threads <= 128 ? tasp_fast_kernel<128> : p.threads <= 256 ? tasp_fast_kernel<256> : p.threads <= 512 ? tasp_fast_kernel<512> : tasp_fast_kernel<1024>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, p.threads, p.smem_bytes, s>>>(T, g, io);

@@ -150,6 +150,8 @@ class Decoder:
                      2: "%s (code-specialised, ahead of time)", 3: "%s (code-specialised, NVRTC)"}.get(d["fast"], "?")
         if d["fast"] == 1 and self.decoder_id == TASP_DEC:
             d["name"] = "tasp_fast_kernel (table-driven, double, lambda messages in tensor memory)"
+        if d["fast"] == 1 and self.decoder_id == ASP_DEC:
+            d["name"] = "asp_fast_kernel (table-driven, double, messages in tensor memory)"
         if "%s" in d["name"]:
             d["name"] %= {LMS_DEC: "lms_tmem" if d["tmem"] else "lms_spec", MS_DEC: "ms_tmem<float>" if d["tmem"] else "ms_spec<float>", IMS_DEC: "ms_tmem<int>" if d["tmem"] else "ms_spec<int>"}.get(self.decoder_id, "spec")
         return d

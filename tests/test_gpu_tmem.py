@@ -41,21 +41,25 @@ def test_tmem_kernel_equals_register_kernel(ldpc, po, monkeypatch, dec, prec, co
     assert np.array_equal(fixed["iters"], a["iters"])                    # fixed-iteration mode reports the first success
 
 
-def test_tasp_fast_equals_parity_kernel(ldpc, po, monkeypatch):
+@pytest.mark.parametrize("dec", ["TASP", "ASP"])
+def test_sumprod_fast_equals_parity_kernel(ldpc, po, monkeypatch, dec):
+    did = getattr(po, dec)
     for code, Z, snr in [("ref32x16_b", 126, 2.0), ("c4_wifi_12x24", 81, 1.5), ("ref32x16_b", 256, 2.0)]:
         hd, llr = _llr(code, Z, snr, 200, 33)
         llr = llr.astype(np.float64)
         monkeypatch.delenv("LDPCB200_NO_TASP_FAST", raising=False)
-        with ldpc.Decoder(hd, Z, po.TASP) as d:
+        with ldpc.Decoder(hd, Z, did) as d:
             assert d.kernel_info()["tmem"], d.kernel_info()
             a = d.decode(llr, 30, want_post=True)
+            fixed = d.decode(llr, 30, no_early_exit=True)
         monkeypatch.setenv("LDPCB200_NO_TASP_FAST", "1")
-        with ldpc.Decoder(hd, Z, po.TASP) as d:
+        with ldpc.Decoder(hd, Z, did) as d:
             assert d.kernel_info()["fast"] == 0
             b = d.decode(llr, 30, want_post=True)
         assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["hard"], b["hard"])
         assert np.array_equal(a["post"], b["post"])                       # same expressions, same order: bitwise
-        want = po.orc_decode(po.TASP, hd, Z, llr[:60], 30)
+        assert np.array_equal(fixed["iters"], a["iters"])
+        want = po.orc_decode(did, hd, Z, llr[:60], 30)
         assert np.array_equal(a["iters"][:60], want["iters"]) and np.array_equal(a["hard"][:60], want["hard"])
 
 
