@@ -102,16 +102,92 @@ __device__ __forceinline__ void tf_row(double* gam, const unsigned* etab, int e0
     tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
 }
 
-template <int RW>
-__device__ __noinline__ void tf_row_call(double* gam, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+// ---- LCHE_DEC (lche_decod, decoders.cpp:2893-3010): the other layered sum-product decoder, LLR domain with three
+// 32-entry look-up tables for log tanh (logexp_int :2777-2836).  Same kernel skeleton as TASP_DEC: messages st[] in
+// tensor memory, posteriors so[] in shared memory, block rows templated on their weight; the tables are copied to
+// shared memory (a per-lane index into __constant__ memory would serialise).
+__constant__ double LF_A[32] = {
+    1.41e+00, 7.72e-01, 4.54e-01, 2.72e-01, 1.65e-01, 9.97e-02, 6.04e-02, 3.66e-02,
+    2.22e-02, 1.35e-02, 8.17e-03, 4.96e-03, 3.01e-03, 1.82e-03, 1.11e-03, 6.71e-04,
+    4.07e-04, 2.47e-04, 1.50e-04, 9.08e-05, 5.51e-05, 3.34e-05, 2.03e-05, 1.23e-05,
+    7.45e-06, 4.52e-06, 2.74e-06, 1.66e-06, 1.01e-06, 6.12e-07, 3.71e-07, 2.25e-07 };
+__constant__ double LF_B[32] = {
+    3.47, 2.77, 2.37, 2.08, 1.86, 1.69, 1.54, 1.41, 1.29, 1.19, 1.11, 1.03, 0.95, 0.89, 0.83, 0.77,
+    0.72, 0.67, 0.63, 0.59, 0.55, 0.52, 0.48, 0.45, 0.43, 0.40, 0.37, 0.35, 0.33, 0.31, 0.29, 0.27 };
+__constant__ double LF_C[32] = {
+    6.93, 6.24, 5.83, 5.55, 5.32, 5.14, 4.99, 4.85, 4.73, 4.63, 4.53, 4.45, 4.37, 4.29, 4.22, 4.16,
+    4.10, 4.04, 3.99, 3.94, 3.89, 3.84, 3.80, 3.75, 3.71, 3.67, 3.64, 3.60, 3.56, 3.53, 3.50, 3.47 };
+
+// tab = A | B | C (96 doubles in shared memory)
+__device__ __forceinline__ double lf_logexp_int(const double* tab, double x)     // :2777-2836
 {
-    tf_row<RW>(gam, etab, e0, n, Z, active, trow);
+    if (x <= 0) x = 1.0 / 4096.0;
+    if (x > 16.0) x = 16.0;
+    if (x >= 2.0) return -tab[(int)(2 * x + 0.5) - 1];
+    else if (x > 1.0 / 16.0) return -tab[32 + (int)(16 * x + 0.5) - 1];
+    else if (x > 1.0 / 512.0) return -tab[64 + (int)(512 * x + 0.5) - 1];
+    else {
+        double s = 0;
+        while (x < 1.0 / 512.0) { x *= 32; s -= 3.46; }
+        return s - tab[64 + (int)(512 * x + 0.5) - 1];
+    }
 }
 
-__device__ __forceinline__ void tf_dispatch(int cnt, double* gam, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+template <int RW>
+__device__ __forceinline__ void lf_row(double* so, const double* tab, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    unsigned lw[2 * RW];
+    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    int idx[RW];
+    double x[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)(pk >> 16);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        x[q] = so[idx[q]];
+    }
+    tmem_wait_ld<2 * RW>(lw);
+    double u[RW], yv[RW], alog[RW];
+    int sy = 0;
+    double sum = 0;
+#pragma unroll
+    for (int q = 0; q < RW; q++) u[q] = yv[q] = x[q] - __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);   // :2962
+    // map_bin_llr, :2837-2890
+#pragma unroll
+    for (int q = 0; q < RW; q++) sy ^= u[q] < 0;
+#pragma unroll
+    for (int q = 0; q < RW; q++) alog[q] = lf_logexp_int(tab, u[q] < 0.0 ? -u[q] : u[q]);
+#pragma unroll
+    for (int q = 0; q < RW; q++) sum += alog[q];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const int hardb = (u[q] < 0) ^ sy;
+        const double av = lf_logexp_int(tab, alog[q] - sum);
+        u[q] = (2 * hardb - 1) * av;
+    }
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        if (active) so[idx[q]] = u[q] + yv[q];                                   // :2979
+        lw[2 * q] = (unsigned)__double2loint(u[q]);
+        lw[2 * q + 1] = (unsigned)__double2hiint(u[q]);
+    }
+    tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+}
+
+template <int RW, bool LCHE>
+__device__ __noinline__ void tf_row_call(double* gam, const double* tab, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    if constexpr (LCHE) lf_row<RW>(gam, tab, etab, e0, n, Z, active, trow);
+    else tf_row<RW>(gam, etab, e0, n, Z, active, trow);
+}
+
+template <bool LCHE>
+__device__ __forceinline__ void tf_dispatch(int cnt, double* gam, const double* tab, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
 {
     switch (cnt) {
-#define TF_CASE(k) case k: tf_row_call<k>(gam, etab, e0, n, Z, active, trow); break;
+#define TF_CASE(k) case k: tf_row_call<k, LCHE>(gam, tab, etab, e0, n, Z, active, trow); break;
     TF_CASE(2) TF_CASE(3) TF_CASE(4) TF_CASE(5) TF_CASE(6) TF_CASE(7) TF_CASE(8) TF_CASE(9) TF_CASE(10) TF_CASE(11)
     TF_CASE(12) TF_CASE(13) TF_CASE(14) TF_CASE(15) TF_CASE(16) TF_CASE(17) TF_CASE(18) TF_CASE(19) TF_CASE(20)
 #undef TF_CASE
@@ -119,7 +195,8 @@ __device__ __forceinline__ void tf_dispatch(int cnt, double* gam, const unsigned
     }
 }
 
-// syndrome of the decisions gamma > 0.5 (check_syndrome_thr, decoders.cpp:2274): every lane XORs its rows
+// syndrome of the decisions gamma > 0.5 (check_syndrome_thr, decoders.cpp:2274) or, for LCHE_DEC, so < 0: every lane XORs its rows
+template <bool LCHE = false>
 __device__ __forceinline__ int tf_syndrome(const double* gam, const unsigned* etab, const int* rpw, int b, int Z, int n, bool active)
 {
     int bad = 0;
@@ -130,7 +207,8 @@ __device__ __forceinline__ int tf_syndrome(const double* gam, const unsigned* et
                 const unsigned pk = etab[e];
                 int k = n + (int)((pk >> 16) & 0x7fffu);
                 if (k >= Z) k -= Z;
-                s ^= (int)(gam[(int)(pk & 0xffffu) + k] > 0.5);
+                const double v = gam[(int)(pk & 0xffffu) + k];
+                s ^= LCHE ? (int)(v < 0) : (int)(v > 0.5);
             }
             bad |= s;
         }
@@ -138,13 +216,14 @@ __device__ __forceinline__ int tf_syndrome(const double* gam, const unsigned* et
     return __syncthreads_or(bad);
 }
 
-template <int MAXT>
+template <int MAXT, bool LCHE>
 __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
 {
     extern __shared__ __align__(16) double tf_smem[];
     const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
-    double* gam = tf_smem;
-    unsigned* etab = (unsigned*)(gam + N);
+    double* gam = tf_smem;                                      // TASP: posteriors P(bit = 1); LCHE: posterior LLRs so[]
+    double* tab = gam + N;                                      // LCHE: the three look-up tables
+    unsigned* etab = (unsigned*)(tab + 96);
     int* rpw = (int*)(etab + E);
     unsigned* s_t = (unsigned*)(rpw + b + 1);
     const bool active = tid < Z;
@@ -153,6 +232,7 @@ __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, con
 
     for (int e = tid; e < E; e += nt) etab[e] = (unsigned)(g.col[e] * Z) | ((unsigned)g.sh[e] << 16);
     for (int j = tid; j <= b; j += nt) rpw[j] = g.rp[j];
+    for (int i = tid; i < 96; i += nt) tab[i] = i < 32 ? LF_A[i] : i < 64 ? LF_B[i - 32] : LF_C[i - 64];
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"((unsigned)__cvta_generic_to_shared(s_t)), "r"((unsigned)T.tcols) : "memory");
@@ -168,14 +248,14 @@ __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, con
     for (;;) {
         const int f = next_frame(io);
         if (f >= io.nf) break;
-        for (int i = tid; i < N; i += nt) gam[i] = tf_llr_to_p1(load_llr(io, N, f, i));          // :2611-2646
-        {   // lambda = 0.5 for every edge (:2620-2641): 0x3FE0000000000000
-            unsigned half[2] = { 0u, 0x3FE00000u };
+        for (int i = tid; i < N; i += nt) gam[i] = LCHE ? load_llr(io, N, f, i) : tf_llr_to_p1(load_llr(io, N, f, i));   // :2611-2646 / :2916
+        {   // TASP: lambda = 0.5 for every edge (:2620-2641), 0x3FE0000000000000; LCHE: st = 0 (:2913-2915)
+            unsigned half[2] = { 0u, LCHE ? 0u : 0x3FE00000u };
             for (int e = 0; e < E; e++) TmemRow<2>::st(trow + 2u * (unsigned)e, half);
             tmem_wait_st();
         }
         __syncthreads();
-        int synd = tf_syndrome(gam, etab, rpw, b, Z, n, active);                                 // :2653
+        int synd = tf_syndrome<LCHE>(gam, etab, rpw, b, Z, n, active);                           // :2653 / :2927-2931
         int ret = 0, locked = 0, steps = 0;
         if (!synd) { locked = 1; ret = 0; }                                                      // :2654-2660
         if (synd || noexit) {
@@ -183,18 +263,18 @@ __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, con
                 tmem_wait_st();
                 for (int j = 0; j < b; j++) {
                     const int e0 = rpw[j];
-                    tf_dispatch(rpw[j + 1] - e0, gam, etab, e0, n, Z, active, trow);
+                    tf_dispatch<LCHE>(rpw[j + 1] - e0, gam, tab, etab, e0, n, Z, active, trow);
                     __syncthreads();
                 }
                 // the reference re-checks after every layer (:2723); only the last verdict is used (:2733)
-                synd = tf_syndrome(gam, etab, rpw, b, Z, n, active);
+                synd = tf_syndrome<LCHE>(gam, etab, rpw, b, Z, n, active);
                 steps++;
                 if (!synd) { if (!locked) { ret = steps; locked = 1; } if (!noexit) break; }
             }
         }
         if (!locked) ret = synd ? -steps : steps;                                                // :2740-2743
         for (int i = tid; i < N; i += nt) store_post(io, N, f, i, gam[i]);
-        emit_frame(g, io, f, ret, [&](int i) { return (int)(gam[i] > 0.5); });                   // :2738
+        emit_frame(g, io, f, ret, [&](int i) { return LCHE ? (int)(gam[i] < 0.0) : (int)(gam[i] > 0.5); });   // :2738 / :3003
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -371,13 +451,13 @@ __global__ void __launch_bounds__(MAXT, 1) asp_fast_kernel(const TaspTab T, cons
 
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
-// decoder_id: LDPCB200_TASP_DEC or LDPCB200_ASP_DEC
+// decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC or LDPCB200_ASP_DEC
 FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block)
 {
     FastPlan p;
     const char* off = getenv("LDPCB200_NO_TASP_FAST");
     if (off && *off == '1') return p;
-    if (g.maxdeg > TASP_MAXDEG || g.mindeg < 2 || g.N > 65535 || g.Z > 1024) return p;
+    if (g.maxdeg > TASP_MAXDEG || g.mindeg < 2 || g.N > 65535 || g.Z > 1024) return p;   // (mindeg: map_bin; the row functions start at weight 2)
     const bool asp = decoder_id == LDPCB200_ASP_DEC;
     if (asp && g.all_cw_2) { p.note = "all columns have weight 2: the reference's shortcut arithmetic stays on the parity kernel"; return p; }
     for (int i = 0; asp && i < g.c; i++)
@@ -386,7 +466,7 @@ FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int sm
     int tcols = 32;
     while (tcols < 2 * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;
     if (tcols > 512) { p.note = "the lambda messages (2 columns per edge) do not fit tensor memory"; return p; }
-    const size_t smem = sizeof(double) * (size_t)g.N * (asp ? 3 : 1) + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
+    const size_t smem = sizeof(double) * ((size_t)g.N * (asp ? 3 : 1) + 96) + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
     if (smem > (size_t)smem_per_block) return p;
     int m = 512 / tcols;
     m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));
@@ -409,8 +489,10 @@ cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, 
     void (*kern)(const TaspTab, const QcDev, const FrameIO);
     if (decoder_id == LDPCB200_ASP_DEC)
         kern = p.threads <= 128 ? asp_fast_kernel<128> : p.threads <= 256 ? asp_fast_kernel<256> : p.threads <= 512 ? asp_fast_kernel<512> : asp_fast_kernel<1024>;
+    else if (decoder_id == LDPCB200_LCHE_DEC)
+        kern = p.threads <= 128 ? tasp_fast_kernel<128, true> : p.threads <= 256 ? tasp_fast_kernel<256, true> : p.threads <= 512 ? tasp_fast_kernel<512, true> : tasp_fast_kernel<1024, true>;
     else
-        kern = p.threads <= 128 ? tasp_fast_kernel<128> : p.threads <= 256 ? tasp_fast_kernel<256> : p.threads <= 512 ? tasp_fast_kernel<512> : tasp_fast_kernel<1024>;
+        kern = p.threads <= 128 ? tasp_fast_kernel<128, false> : p.threads <= 256 ? tasp_fast_kernel<256, false> : p.threads <= 512 ? tasp_fast_kernel<512, false> : tasp_fast_kernel<1024, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, p.threads, p.smem_bytes, s>>>(T, g, io);

@@ -150,6 +150,8 @@ class Decoder:
                      2: "%s (code-specialised, ahead of time)", 3: "%s (code-specialised, NVRTC)"}.get(d["fast"], "?")
         if d["fast"] == 1 and self.decoder_id == TASP_DEC:
             d["name"] = "tasp_fast_kernel (table-driven, double, lambda messages in tensor memory)"
+        if d["fast"] == 1 and self.decoder_id == LCHE_DEC:
+            d["name"] = "tasp_fast_kernel<LCHE> (table-driven, double, messages in tensor memory)"
         if d["fast"] == 1 and self.decoder_id == ASP_DEC:
             d["name"] = "asp_fast_kernel (table-driven, double, messages in tensor memory)"
         if "%s" in d["name"]:
