@@ -72,44 +72,75 @@ __device__ __forceinline__ float bpsk_llr(const ChannelParams& ch, float n)
     return __fmul_rn(__fmaf_rn(-ch.sigma, n, 1.0f), ch.llr_scale);
 }
 
+// n / d, correctly rounded (IEEE round-to-nearest, the reference's x86 divsd), WITHOUT the range-check branch and the
+// slow-path call that the compiler attaches to every double division: the instruction sequence of nvcc's own fast path
+// (MUFU.RCP64H seed, two Newton steps on the reciprocal, one residual correction of the quotient), which is exact
+// whenever both operands and the quotient are normal numbers far from the exponent limits (or n = 0).  Callers state
+// why that holds: TASP_DEC (tasp_fast.cu): d is a sum of products of probabilities clamped to [1e-4, 1 - 1e-4]
+// (1e-8 < d <= 1), 0 <= n <= 1 with n >= e^-160; ASP_DEC (dec_sumprod.cu): messages clamped to [1e-6, 1 - 1e-6], column
+// products of at most LDPCB200_MAX_ROW_WEIGHT such factors times a prior >= e^-40; Demodulate (pam_demod below): squared
+// distances over N0, likelihoods that are 0 or >= e^-T over their sum, ratios of such sums (0 / 0 gives NaN like the
+// reference's division).
+// Straight-line code lets the scheduler interleave the independent divisions of a block row / a sweep; with the branch
+// each division was its own basic block and the kernels sat in fixed-latency stalls.  tests/test_gpu_tmem.py checks
+// tasp_fast's posteriors bitwise against the parity kernel, which divides with operator /.
+__device__ __forceinline__ double div_normal(double n, double d)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = __fma_rn(-d, y, 1.0);
+    e = __fma_rn(e, e, e);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-d, y, 1.0);
+    y = __fma_rn(y, e, y);
+    const double q = __dmul_rn(n, y);
+    const double r = __fma_rn(-d, q, n);
+    return __fma_rn(y, r, q);
+}
+
 // one output of Demodulate's if-ladder (e.g. QAM_demodulator.cpp:215-239)
 __device__ __forceinline__ double demod_out(double p0, double p1, double T, int out_type)
 {
     if (p0 == 0.0) return out_type == 0 ? T : 1.0;
     if (p1 == 0.0) return out_type == 0 ? -T : 0.0;
-    return out_type == 0 ? log(p1 / p0) : p1;
+    return out_type == 0 ? log(div_normal(p1, p0)) : p1;
 }
 
 // Exact bit metrics of one PAM component (I or Q) of a Gray-mapped QAM symbol, m = 4, 6 or 8 bits per
 // symbol: o[0 .. m/2) in the order Demodulate writes them.  Evaluation order follows
 // QAM_demodulator.cpp:181-199 (t = x - L; t *= t; t /= N0; P normalised before the bit sums) and the
 // summation trees of :203-561, so only exp/log can differ from the reference, in the last ulp.
-__device__ __forceinline__ void pam_demod(double x, double N0, double T, int m, int out_type, double* o)
+template <int SQ>
+__device__ __forceinline__ void pam_likelihoods(double x, double N0, double T, double (&P)[16])
 {
-    const int SQ = 1 << (m >> 1);
-    double P[16];
     double sum = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        if (i < SQ) {
-            double t = x - (double)(2 * i - (SQ - 1));
-            t *= t;
-            t /= N0;
-            P[i] = t < T ? exp(-t) : 0.0;
-            sum += P[i];
-        } else P[i] = 0.0;
+    for (int i = 0; i < SQ; i++) {
+        double t = x - (double)(2 * i - (SQ - 1));
+        t *= t;
+        t = div_normal(t, N0);                                   // t /= N0, :183
+        P[i] = t < T ? exp(-t) : 0.0;
+        sum += P[i];
     }
 #pragma unroll
-    for (int i = 0; i < 16; i++) if (i < SQ) P[i] /= sum;
+    for (int i = 0; i < SQ; i++) P[i] = div_normal(P[i], sum);   // :196-199
+}
+
+__device__ __forceinline__ void pam_demod(double x, double N0, double T, int m, int out_type, double* o)
+{
+    double P[16];
     if (m == 4) {
+        pam_likelihoods<4>(x, N0, T, P);
         o[0] = demod_out(P[0] + P[1], P[2] + P[3], T, out_type);
         o[1] = demod_out(P[0] + P[3], P[1] + P[2], T, out_type);
     } else if (m == 6) {
+        pam_likelihoods<8>(x, N0, T, P);
         double p12 = P[0] + P[1], p34 = P[2] + P[3], p56 = P[4] + P[5], p78 = P[6] + P[7];
         o[0] = demod_out(p12 + p34, p56 + p78, T, out_type);
         o[1] = demod_out(p12 + p78, p34 + p56, T, out_type);
         o[2] = demod_out(P[0] + P[3] + P[4] + P[7], P[1] + P[2] + P[5] + P[6], T, out_type);
     } else {
+        pam_likelihoods<16>(x, N0, T, P);
         double p12 = P[0] + P[1], p34 = P[2] + P[3], p56 = P[4] + P[5], p78 = P[6] + P[7];
         double p9A = P[8] + P[9], pBC = P[10] + P[11], pDE = P[12] + P[13], pFG = P[14] + P[15];
         double p1234 = p12 + p34, p5678 = p56 + p78, p9ABC = p9A + pBC, pDEFG = pDE + pFG;
