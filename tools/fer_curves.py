@@ -55,17 +55,34 @@ RUNS = [
 
 
 def main():
+    """Under torchrun (one rank per GPU) the frames of every point are striped over the ranks (simhost.frame_loop: one
+    all-reduce of four counters per round); results do not depend on the number of ranks.  FIXED_FRAMES=n in the
+    environment decodes exactly n frames per point instead of stopping at the error count (timing runs)."""
     out = []
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    group = device = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    fixed = int(os.environ.get("FIXED_FRAMES", "0"))
     for label, code, Z, dec, prec, maxiter, snrs, nerr, nmax, ref in RUNS:
         if only and only not in label:
             continue
         hd, _ = load_code(code)
         pts = []
-        with L.Decoder(hd, Z, getattr(L, dec), precision=prec, use_fast=2) as d:
+        if fixed:
+            nerr, nmax = 1 << 62, fixed - 1
+        with L.Decoder(hd, Z, getattr(L, dec), precision=prec, use_fast=2, device=local) as d:
             for k, snr in enumerate(snrs):
                 t0 = time.perf_counter()
-                ber, fer, r = SH.bp_simulation(d, maxiter, nerr, nmax, snr, 1.0, seed=1, stream=k, round_frames=1 << 14, max_round_frames=1 << 20)
+                ber, fer, r = SH.bp_simulation(d, maxiter, nerr, nmax, snr, 1.0, seed=1, stream=k, round_frames=1 << 14, max_round_frames=1 << 20,
+                                               group=group, device=device)
                 pt = {"snr_db": snr, "fer": fer, "ber": ber, "frames": r.experiment, "frame_errors": r.nde, "undetected": r.nue,
                       "seconds": round(time.perf_counter() - t0, 2)}
                 if ref:
@@ -73,9 +90,14 @@ def main():
                     mylo, myhi = wilson(r.nde, r.experiment)
                     pt.update(reference_fer=ref[k], reference_ci95=[lo, hi], inside=bool(myhi >= lo and mylo <= hi))
                 pts.append(pt)
-                print(label, pt, file=sys.stderr)
+                if rank == 0:
+                    print(label, pt, file=sys.stderr)
             out.append({"case": label, "kernel": d.kernel_info()["name"], "points": pts})
-    print(json.dumps({"runs": out, "note": "stop rule: n frame errors or the frame budget, applied in frame order (simhost.frame_loop)"}, indent=1))
+    if rank == 0:
+        print(json.dumps({"runs": out, "n_gpus": world,
+                          "note": "stop rule: n frame errors or the frame budget, applied in frame order (simhost.frame_loop)"}, indent=1))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
