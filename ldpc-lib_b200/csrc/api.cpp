@@ -167,8 +167,10 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
         CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream));
     } else if (is_minsum(h->decoder_id)) {
+        CU(h->ws.reserve(h->smem_ws ? 256 : h->ws_stride * h->grid));
         CU(launch_minsum_generic(h->decoder_id, h->p.precision, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, h->smem_ws, grid, h->nt, h->stream));
     } else {
+        CU(h->ws.reserve(h->smem_ws ? 256 : h->ws_stride * h->grid));
         CU(launch_sumprod_generic(h->decoder_id, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, h->smem_ws, grid, h->nt, h->stream));
     }
     h->last_launches++;
@@ -302,7 +304,7 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
             per_sm = std::min(per_sm, h->nt == 256 ? 2 : 1);
             h->grid = h->num_sms * std::max(per_sm, 1);
         }
-        CU(h->ws.reserve(h->smem_ws ? 256 : h->ws_stride * h->grid));
+        // (the table-driven kernels' workspace is allocated by the first launch that needs it: launch_decoder)
         CU(h->counters.reserve(8 * sizeof(unsigned long long)));
         CU(h->next.reserve(256));
         CU(h->bpsynd.reserve((size_t)h->g.R + 16));

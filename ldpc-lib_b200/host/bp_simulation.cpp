@@ -93,17 +93,30 @@ std::pair<double, double> bp_simulation(
     // compile a code-specialised kernel for this matrix unless told not to (LDPCB200_JIT=0); cached per process
     const char* je = getenv("LDPCB200_JIT");
     p.use_fast = (je && atoi(je) == 0) ? 1 : 2;
-    std::vector<ldpcb200_handle> eng;
-    std::vector<int> devs = devices_from_env();
-    for (size_t k = 0; k < devs.size(); k++) {
-        ldpcb200_handle h = NULL;
-        p.device = devs[k];
-        int rc = ldpcb200_create(hd.data(), b, c, M, decoder_type, &p, &h);
-        if (rc) {
-            if (getenv("LDPCB200_DEVICES") && std::string(getenv("LDPCB200_DEVICES")) == "all" && !eng.empty()) break;
-            die("bp_simulation: cannot open the decoder on device %d: %s", devs[k], ldpcb200_last_error());
+    // The engine handles (one per GPU) are kept between calls: an SNR sweep calls bp_simulation() once per point with the
+    // same matrix and decoder, and opening a handle (streams, tables, launch plan, possibly a run-time compilation)
+    // costs more than a short point.  A different matrix / decoder / lifting replaces the cached set.
+    static std::vector<ldpcb200_handle> eng;
+    static std::vector<int16_t> eng_hd;
+    static int eng_key[6] = { -1, -1, -1, -1, -1, -1 };
+    static std::string eng_devs;
+    const char* de = getenv("LDPCB200_DEVICES");
+    const int key[6] = { b, c, M, decoder_type, p.precision, p.use_fast };
+    if (eng.empty() || eng_hd != hd || memcmp(eng_key, key, sizeof key) != 0 || eng_devs != (de ? de : "")) {
+        for (auto h : eng) ldpcb200_destroy(h);
+        eng.clear();
+        std::vector<int> devs = devices_from_env();
+        for (size_t k = 0; k < devs.size(); k++) {
+            ldpcb200_handle h = NULL;
+            p.device = devs[k];
+            int rc = ldpcb200_create(hd.data(), b, c, M, decoder_type, &p, &h);
+            if (rc) {
+                if (de && std::string(de) == "all" && !eng.empty()) break;
+                die("bp_simulation: cannot open the decoder on device %d: %s", devs[k], ldpcb200_last_error());
+            }
+            eng.push_back(h);
         }
-        eng.push_back(h);
+        eng_hd = hd; memcpy(eng_key, key, sizeof key); eng_devs = de ? de : "";
     }
     const int G = (int)eng.size();
 
@@ -173,8 +186,6 @@ std::pair<double, double> bp_simulation(
         g_next_frame += (unsigned long long)want;
         per_gpu = std::min<long long>(per_gpu * 4, 1 << 18);
     }
-    for (auto h : eng) ldpcb200_destroy(h);
-
     g_stats.frames_counted = experiment; g_stats.frames_decoded = decoded; g_stats.frame_errors = nde;
     g_stats.info_bit_errors = nse; g_stats.undetected = nue; g_stats.gpu_ms = gpu_ms; g_stats.gpus = G;
     g_stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
