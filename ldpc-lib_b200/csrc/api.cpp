@@ -163,7 +163,7 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
     } else if (use_fast && (h->decoder_id == LDPCB200_IMS_DEC || h->decoder_id == LDPCB200_MS_DEC)) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
         CU(launch_ms_fast(h->fast, h->dp, io, std::max(fgrid, 1), h->stream));
-    } else if (use_fast && (h->decoder_id == LDPCB200_TASP_DEC || h->decoder_id == LDPCB200_ASP_DEC || h->decoder_id == LDPCB200_LCHE_DEC)) {
+    } else if (use_fast && (h->decoder_id == LDPCB200_TASP_DEC || h->decoder_id == LDPCB200_ASP_DEC || h->decoder_id == LDPCB200_LCHE_DEC || h->decoder_id == LDPCB200_IASP_DEC)) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
         CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream));
     } else if (is_minsum(h->decoder_id)) {
@@ -313,7 +313,7 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
             if (decoder_id == LDPCB200_LMS_DEC) h->fast = plan_lms_fast(h->g, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
             else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ms_fast(h->g, 2, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
             else if (decoder_id == LDPCB200_MS_DEC) h->fast = plan_ms_fast(h->g, 1, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
-            else if (decoder_id == LDPCB200_TASP_DEC || decoder_id == LDPCB200_ASP_DEC || decoder_id == LDPCB200_LCHE_DEC) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
+            else if (decoder_id == LDPCB200_TASP_DEC || decoder_id == LDPCB200_ASP_DEC || decoder_id == LDPCB200_LCHE_DEC || decoder_id == LDPCB200_IASP_DEC) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
         }
         return 0;
     }();

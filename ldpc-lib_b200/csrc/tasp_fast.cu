@@ -327,22 +327,25 @@ __device__ __noinline__ void af_rowR(double* A, double* Bv, const double* prior,
     tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
 }
 
-template <int RW>
-__device__ __noinline__ void af_rowE(const double* A, const unsigned* etab, int e0, int n, int Z, unsigned trow)
+// sweep E needs no row structure: a flat loop over the edges, four at a time (one tcgen05.ld / st group per four edges),
+// keeps the code small -- the row-templated form was 19 unrolled copies of the three divisions per edge, and four
+// CTAs at different places of it stalled on instruction fetch
+template <int NE>
+__device__ __forceinline__ void af_edgesE(const double* A, const unsigned* etab, int e, int n, int Z, unsigned trow)
 {
-    unsigned lw[2 * RW];
-    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
-    double s1[RW];
+    unsigned lw[2 * NE];
+    tmem_ld_n<2 * NE>(trow + 2u * (unsigned)e, lw);
+    double s1[NE];
 #pragma unroll
-    for (int q = 0; q < RW; q++) {
-        const unsigned pk = etab[e0 + q];
+    for (int q = 0; q < NE; q++) {
+        const unsigned pk = etab[e + q];
         int k = n + (int)((pk >> 16) & 0x7fffu);
         if (k >= Z) k -= Z;
         s1[q] = A[(int)(pk & 0xffffu) + k];
     }
-    tmem_wait_ld<2 * RW>(lw);
+    tmem_wait_ld<2 * NE>(lw);
 #pragma unroll
-    for (int q = 0; q < RW; q++) {
+    for (int q = 0; q < NE; q++) {
         const double sos = __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);
         const double p1 = div_normal(s1[q], sos);                                // :2537-2550
         const double p0 = div_normal(1 - s1[q], 1 - sos);
@@ -351,7 +354,15 @@ __device__ __noinline__ void af_rowE(const double* A, const unsigned* etab, int 
         lw[2 * q] = (unsigned)__double2loint(d);
         lw[2 * q + 1] = (unsigned)__double2hiint(d);
     }
-    tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    tmem_st_n<2 * NE>(trow + 2u * (unsigned)e, lw);
+}
+__device__ __noinline__ void af_sweepE(const double* A, const unsigned* etab, int E, int n, int Z, unsigned trow)
+{
+    int e = 0;
+#pragma unroll 1
+    for (; e + 4 <= E; e += 4) af_edgesE<4>(A, etab, e, n, Z, trow);
+#pragma unroll 1
+    for (; e < E; e++) af_edgesE<1>(A, etab, e, n, Z, trow);
 }
 
 #define AF_CASES(CALL) \
@@ -421,15 +432,7 @@ __global__ void __launch_bounds__(MAXT, 1) asp_fast_kernel(const TaspTab T, cons
                 for (int i = tid; i < N; i += nt) A[i] = div_normal(A[i], Bv[i] + A[i]);         // sweep V, :2522
                 __syncthreads();
                 tmem_wait_st();
-                for (int j = 0; j < b; j++) {                                                    // sweep E
-                    const int e0 = rpw[j];
-                    switch (rpw[j + 1] - e0) {
-#define AF_E(k) case k: af_rowE<k>(A, etab, e0, n, Z, trow); break;
-                    AF_CASES(AF_E)
-#undef AF_E
-                    default: break;
-                    }
-                }
+                af_sweepE(A, etab, E, n, Z, trow);                                               // sweep E
                 tmem_wait_st();
                 synd = tf_syndrome(A, etab, rpw, b, Z, n, active);                               // :2566
                 steps++;
@@ -449,29 +452,259 @@ __global__ void __launch_bounds__(MAXT, 1) asp_fast_kernel(const TaspTab T, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// IASP_DEC (isum_prod_gf2_decod_qc_lm, decoders.cpp:3822-4121): the 12-bit fixed-point version of ASP_DEC, bit-exact.
+// The sweeps of asp_fast_kernel in the reference's integer arithmetic: messages are 12-bit values, ONE TMEM word per
+// edge and lane; the per-bit products P1 / P0 are 32-bit words in shared memory, multiplied in ascending block-row order
+// from the check side (64-bit products shifted right by 16, :4003-4016); rounding shifts are DIVR (div_power2r :80).
+#define IF_ONE 4096
+#define IF_MAX 4095
+#define IF_DIVR(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+
+template <int RW>
+__device__ __forceinline__ void if_imap_bin(int (&s)[RW])                        // imap_bin :2235-2271, s[] are uint16 values
+{
+    short SF[RW], SB[RW], P[RW];
+#pragma unroll
+    for (int i = 0; i < RW; i++) P[i] = (short)(IF_ONE - 2 * s[i]);
+    SF[0] = P[0];
+#pragma unroll
+    for (int i = 1; i < RW - 1; i++) SF[i] = (short)IF_DIVR((int)P[i] * SF[i - 1], 12);
+    SB[RW - 1] = P[RW - 1];
+#pragma unroll
+    for (int i = RW - 2; i > 0; i--) SB[i] = (short)IF_DIVR((int)P[i] * SB[i + 1], 12);
+    s[0] = (unsigned short)IF_DIVR(IF_ONE - SB[1], 1);
+    s[0] = s[0] < 1 ? 1 : s[0];
+#pragma unroll
+    for (int i = 1; i < RW - 1; i++) {
+        const int Zv = IF_DIVR((int)SF[i - 1] * SB[i + 1], 12);
+        s[i] = (unsigned short)IF_DIVR(IF_ONE - Zv, 1);
+        s[i] = s[i] < 1 ? 1 : s[i];
+    }
+    s[RW - 1] = (unsigned short)IF_DIVR(IF_ONE - SF[RW - 2], 1);
+    s[RW - 1] = s[RW - 1] < 1 ? 1 : s[RW - 1];
+}
+
+template <int RW>
+__device__ __noinline__ void if_rowR(unsigned* A, unsigned* Bv, const unsigned* yq, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    unsigned lw[RW];
+    tmem_ld_n<RW>(trow + (unsigned)e0, lw);
+    int idx[RW];
+    unsigned P1[RW], P0[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];                                        // bit offset | shift << 16 | first-of-column << 31
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        if (pk >> 31) { const unsigned y = yq[idx[q]]; P1[q] = y << 16; P0[q] = (unsigned)((IF_ONE << 4) - y) << 16; }   // :3987-3988
+        else { P1[q] = A[idx[q]]; P0[q] = Bv[idx[q]]; }
+    }
+    tmem_wait_ld<RW>(lw);
+    int a[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) a[q] = (int)lw[q];
+    if_imap_bin<RW>(a);                                                          // :3906-3911
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned d = (unsigned)a[q] & 0xffffu;
+        const unsigned d1 = (d << 4) & 0xffffu;                                  // (uint16)(d << 4), :4008
+        const unsigned d0 = ((unsigned)(IF_MAX - (int)d) << 4) & 0xffffu;        // MAX_SOFT, not ONE_SOFT (:4010)
+        if (active) {
+            A[idx[q]] = (unsigned)(((unsigned long long)P1[q] * d1) >> 16);      // :4011-4016
+            Bv[idx[q]] = (unsigned)(((unsigned long long)P0[q] * d0) >> 16);
+        }
+        lw[q] = d;
+    }
+    tmem_st_n<RW>(trow + (unsigned)e0, lw);
+}
+
+template <int NE>
+__device__ __forceinline__ void if_edgesE(const unsigned* A, const unsigned* etab, int e, int n, int Z, unsigned trow)
+{
+    unsigned lw[NE];
+    tmem_ld_n<NE>(trow + (unsigned)e, lw);
+    int so[NE];
+#pragma unroll
+    for (int q = 0; q < NE; q++) {
+        const unsigned pk = etab[e + q];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        so[q] = (int)A[(int)(pk & 0xffffu) + k];
+    }
+    tmem_wait_ld<NE>(lw);
+#pragma unroll
+    for (int q = 0; q < NE; q++) {                                               // :4055-4102
+        const int sv = so[q] << (12 - 4);
+        const int m = (int)lw[q];
+        const int sos = m < 1 ? 1 : m;
+        const int p1 = sv / sos;
+        const int t = (IF_ONE - sos) < 1 ? 1 : (IF_ONE - sos);
+        const int p0 = (IF_ONE * IF_ONE - sv) / t;
+        const int yy = IF_DIVR(p1 + p0, 6);
+        const int y1 = yy < 1 ? 1 : yy;
+        int d = (p1 << 6) / y1;
+        d = d < 1 ? 1 : d;
+        lw[q] = (unsigned)(IF_MAX < d ? IF_MAX : d);
+    }
+    tmem_st_n<NE>(trow + (unsigned)e, lw);
+}
+__device__ __noinline__ void if_sweepE(const unsigned* A, const unsigned* etab, int E, int n, int Z, unsigned trow)
+{
+    int e = 0;
+#pragma unroll 1
+    for (; e + 4 <= E; e += 4) if_edgesE<4>(A, etab, e, n, Z, trow);
+#pragma unroll 1
+    for (; e < E; e++) if_edgesE<1>(A, etab, e, n, Z, trow);
+}
+
+// syndrome of the decisions so >> 15 (icheck_syndrome :3772)
+__device__ __forceinline__ int if_syndrome(const unsigned* so, const unsigned* etab, const int* rpw, int b, int Z, int n, bool active)
+{
+    int bad = 0;
+    if (active) {
+        for (int j = 0; j < b; j++) {
+            unsigned s = 0;
+            for (int e = rpw[j]; e < rpw[j + 1]; e++) {
+                const unsigned pk = etab[e];
+                int k = n + (int)((pk >> 16) & 0x7fffu);
+                if (k >= Z) k -= Z;
+                s ^= so[(int)(pk & 0xffffu) + k] >> 15;
+            }
+            bad |= (int)(s & 1u);
+        }
+    }
+    return __syncthreads_or(bad);
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) iasp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
+{
+    extern __shared__ __align__(16) double tf_smem[];
+    const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
+    unsigned* A = (unsigned*)tf_smem;    // per-bit product P1, then the posterior so (16-bit value)
+    unsigned* Bv = A + N;                // per-bit product P0
+    unsigned* yq = Bv + N;               // quantised prior << 4 (:3867)
+    unsigned* etab = yq + N;
+    int* rpw = (int*)(etab + E);
+    unsigned* s_t = (unsigned*)(rpw + b + 1);
+    const bool active = tid < Z;
+    const int n = active ? tid : Z - 1;
+    const bool noexit = io.flags & LDPCB200_NO_EARLY_EXIT;
+
+    for (int e = tid; e < E; e += nt) {
+        const int c = g.col[e];
+        etab[e] = (unsigned)(c * Z) | ((unsigned)g.sh[e] << 16) | (g.cedge[g.cp[c]] == e ? 0x80000000u : 0u);
+    }
+    for (int j = tid; j <= b; j += nt) rpw[j] = g.rp[j];
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(s_t)), "r"((unsigned)T.tcols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = *(volatile unsigned*)s_t;
+    // one TMEM column per edge, E columns per group of 4 warps
+    const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * E), 0);
+
+    for (;;) {
+        const int f = next_frame(io);
+        if (f >= io.nf) break;
+        for (int i = tid; i < N; i += nt) {                                                      // :3849-3861
+            const double v = tf_maxd(tf_mind(load_llr(io, N, f, i), 20.0), -20.0);
+            const double pr = 1.0 / (1.0 + exp(v));
+            int x = (int)(pr * IF_ONE + 0.5);
+            x = IF_MAX < x ? IF_MAX : x;
+            yq[i] = (unsigned)(x < 1 ? 1 : x);
+        }
+        __syncthreads();
+        for (int e = 0; e < E; e++) {                                                            // msg = 12-bit prior of the edge's bit, :3869-3886
+            const unsigned pk = etab[e];
+            int k = n + (int)((pk >> 16) & 0x7fffu);
+            if (k >= Z) k -= Z;
+            unsigned w[1] = { yq[(int)(pk & 0xffffu) + k] };
+            TmemRow<1>::st(trow + (unsigned)e, w);
+        }
+        tmem_wait_st();
+        __syncthreads();
+        for (int i = tid; i < N; i += nt) { const unsigned y = (yq[i] << 4) & 0xffffu; yq[i] = y; A[i] = y; }   // :3867, :3889
+        __syncthreads();
+        int synd = if_syndrome(A, etab, rpw, b, Z, n, active);
+        int ret = 0, locked = 0, steps = 0;
+        if (!synd) { locked = 1; ret = 0; }
+        if (synd || noexit) {
+            while (steps < io.maxiter) {
+                for (int j = 0; j < b; j++) {                                                    // sweep R
+                    const int e0 = rpw[j];
+                    switch (rpw[j + 1] - e0) {
+#define IF_R(k) case k: if_rowR<k>(A, Bv, yq, etab, e0, n, Z, active, trow); break;
+                    AF_CASES(IF_R)
+#undef IF_R
+                    default: break;
+                    }
+                    __syncthreads();
+                }
+                for (int i = tid; i < N; i += nt) {                                              // sweep V, :4018-4030
+                    unsigned x = A[i] >> 1;
+                    unsigned yv = (Bv[i] >> 1) + x;
+                    const int flg = yv > (unsigned)(IF_ONE << 4);
+                    if (flg) yv = yv >> 12; else x = x << 12;
+                    yv = yv < 1 ? 1 : yv;
+                    int sv = (int)(x / yv);
+                    sv = IF_MAX < sv ? IF_MAX : sv;
+                    sv = sv < 1 ? 1 : sv;
+                    A[i] = ((unsigned)sv << 4) & 0xffffu;
+                }
+                __syncthreads();
+                tmem_wait_st();
+                if_sweepE(A, etab, E, n, Z, trow);                                               // sweep E
+                tmem_wait_st();
+                synd = if_syndrome(A, etab, rpw, b, Z, n, active);
+                steps++;
+                if (!synd) { if (!locked) { ret = steps; locked = 1; } if (!noexit) break; }
+            }
+        }
+        if (!locked) ret = -steps;
+        for (int i = tid; i < N; i += nt) store_post(io, N, f, i, A[i]);
+        emit_frame(g, io, f, ret, [&](int i) { return (int)(A[i] >> 15); });
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)T.tcols) : "memory");
+    }
+}
+
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
-// decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC or LDPCB200_ASP_DEC
+// decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC, LDPCB200_ASP_DEC or LDPCB200_IASP_DEC
 FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block)
 {
     FastPlan p;
     const char* off = getenv("LDPCB200_NO_TASP_FAST");
     if (off && *off == '1') return p;
     if (g.maxdeg > TASP_MAXDEG || g.mindeg < 2 || g.N > 65535 || g.Z > 1024) return p;   // (mindeg: map_bin; the row functions start at weight 2)
-    const bool asp = decoder_id == LDPCB200_ASP_DEC;
+    const bool iasp = decoder_id == LDPCB200_IASP_DEC;
+    const bool asp = decoder_id == LDPCB200_ASP_DEC || iasp;
     if (asp && g.all_cw_2) { p.note = "all columns have weight 2: the reference's shortcut arithmetic stays on the parity kernel"; return p; }
     for (int i = 0; asp && i < g.c; i++)
         if (g.cp[i + 1] == g.cp[i]) return p;                           // sweep R starts a bit's product at its first edge
     const int zp = (g.Z + 31) & ~31;
     int tcols = 32;
-    while (tcols < 2 * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;
+    while (tcols < (iasp ? 1 : 2) * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;        // fp64 messages take two columns, 12-bit ones one
     if (tcols > 512) { p.note = "the lambda messages (2 columns per edge) do not fit tensor memory"; return p; }
-    const size_t smem = sizeof(double) * ((size_t)g.N * (asp ? 3 : 1) + 96) + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
+    const size_t smem = (iasp ? sizeof(unsigned) * 3 * (size_t)g.N : sizeof(double) * ((size_t)g.N * (asp ? 3 : 1) + 96))
+                        + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
     if (smem > (size_t)smem_per_block) return p;
     int m = 512 / tcols;
     m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));
     m = std::min(m, 2048 / zp);
-    m = std::min(m, 65536 / (zp * (zp <= 256 ? 255 : zp <= 512 ? 128 : 64)));     // register budget of the instance (launch_tasp_fast)
+    m = std::min(m, 65536 / (zp * (iasp ? (zp <= 512 ? 128 : 64) : zp <= 256 ? 255 : zp <= 512 ? 128 : 64)));     // register budget of the instance (launch_tasp_fast)
     if (m < 1) m = 1;
     p.ok = 1; p.variant = 0; p.tmem = 1;
     p.threads = zp; p.frames_per_cta = 1; p.ctas_per_sm = m;
@@ -487,7 +720,9 @@ cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, 
     const TaspTab& T = *reinterpret_cast<const TaspTab*>(p.tab.data());
     // the register budget follows the CTA size: 255 registers per thread up to 256 threads
     void (*kern)(const TaspTab, const QcDev, const FrameIO);
-    if (decoder_id == LDPCB200_ASP_DEC)
+    if (decoder_id == LDPCB200_IASP_DEC)
+        kern = p.threads <= 128 ? iasp_fast_kernel<128, 4> : p.threads <= 256 ? iasp_fast_kernel<256, 2> : p.threads <= 512 ? iasp_fast_kernel<512, 1> : iasp_fast_kernel<1024, 1>;   // <= 128 registers
+    else if (decoder_id == LDPCB200_ASP_DEC)
         kern = p.threads <= 128 ? asp_fast_kernel<128> : p.threads <= 256 ? asp_fast_kernel<256> : p.threads <= 512 ? asp_fast_kernel<512> : asp_fast_kernel<1024>;
     else if (decoder_id == LDPCB200_LCHE_DEC)
         kern = p.threads <= 128 ? tasp_fast_kernel<128, true> : p.threads <= 256 ? tasp_fast_kernel<256, true> : p.threads <= 512 ? tasp_fast_kernel<512, true> : tasp_fast_kernel<1024, true>;
