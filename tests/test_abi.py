@@ -113,3 +113,48 @@ def test_code_specialised_kernel_generates_and_compiles_without_a_gpu():
     with pytest.raises(L.LdpcError) as e:
         L.jit_check(big, 1000)
     assert e.value.code == L.EUNSUPPORTED
+
+
+def test_runtime_generator_emits_the_same_tensor_memory_tables_as_the_build_time_one(tmp_path, monkeypatch):
+    """spec_jit.cpp (run time, any matrix) and tools/gen_lms_spec.py (build time, benchmark matrices) both derive the
+    rotation tables of lms_tmem.cuh / ms_tmem.cuh; they must agree, and the tables must be self-consistent:
+    following DELTA through one iteration returns every column to its ROT."""
+    import re
+    import shutil
+    if not (os.path.exists("/usr/local/cuda/lib64/libnvrtc.so.12") or shutil.which("nvcc")):
+        pytest.skip("NVRTC not installed")
+    import importlib.util
+    from codes import load_code
+    spec = importlib.util.spec_from_file_location("gen_lms_spec", os.path.join(ROOT, "tools", "gen_lms_spec.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    L = load_binding()
+    for code, Z in [("ref32x16_b", 256), ("c4_wifi_12x24", 81), ("ref32x16_a", 126)]:
+        hd, _ = load_code(code)
+        dump = tmp_path / ("%s_%d.cu" % (code, Z))
+        monkeypatch.setenv("LDPCB200_JIT_DUMP", str(dump))
+        monkeypatch.delenv("LDPCB200_NO_TMEM", raising=False)
+        assert L.jit_check(hd, Z) > 10000
+        txt = dump.read_text()
+        assert "LmsTmem<ldpcb200::gen_jit::Code>" in txt                 # these codes take the tensor-memory variant
+
+        def arr(name):
+            m = re.search(r"static constexpr \w+ %s\[\d+\] = \{([^}]*)\}" % name, txt)
+            return [int(x) for x in m.group(1).replace(",", " ").split()]
+        b, c = hd.shape
+        rp, col, sh = [0], [], []
+        for j in range(b):
+            for i in range(c):
+                if hd[j, i] != -1:
+                    col.append(i); sh.append(int(hd[j, i]) % Z)
+            rp.append(len(col))
+        zp = (Z + 31) // 32 * 32
+        rot, delta, ri, synsh, tcols, lastw = gen.tmem_tables(b, c, Z, rp, col, sh, zp)
+        assert arr("DELTA") == delta and arr("ROT") == rot and arr("RI") == ri and arr("SYNSH") == synsh and arr("LAST") == lastw
+        assert int(re.search(r"TCOLS = (\d+)", txt).group(1)) == tcols
+        # one pass over the edges in schedule order: a column read at n + DELTA and rewritten lane-aligned ends rotated by ROT
+        cur = list(rot)
+        for e in range(len(col)):
+            assert (cur[col[e]] + delta[e]) % Z == sh[e]
+            cur[col[e]] = sh[e]
+        assert cur == rot
