@@ -425,6 +425,7 @@ struct LmsTmem {
             const int f = s_misc[0];
             if (f >= io.nf) break;
 
+            bool packed = false;                                 // hb already holds the decisions of the channel values
             if (io.ch.enabled) {
                 const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
                 if (io.ch.m > 2) {
@@ -456,26 +457,30 @@ struct LmsTmem {
                 }
             } else if (io.llr_dtype == 1) {                      // LDPCB200_F32
                 const float* y = (const float*)io.llr + (size_t)f * N;
-                if (ALL_ACTIVE || active) {
+                const bool act = ALL_ACTIVE || active;
 #pragma unroll
-                    for (int c0 = 0; c0 < C; c0 += 16) {         // 16 loads in flight per thread
-                        float x[16];
+                for (int c0 = 0; c0 < C; c0 += 16) {             // 16 loads in flight per thread
+                    float x[16];
 #pragma unroll
-                        for (int u = 0; u < 16; u++) {           // position tid of column col holds bit (tid + ROT) mod Z
-                            const int col = c0 + u;
-                            if (col < C) {
-                                int k = tid + K::rt_rot()[col];
-                                if (k >= Z) k -= Z;
-                                x[u] = __ldcs(y + col * Z + k);
-                            }
+                    for (int u = 0; u < 16; u++) {               // position tid of column col holds bit (tid + ROT) mod Z
+                        const int col = c0 + u;
+                        if (col < C) {
+                            int k = tid + K::rt_rot()[col];
+                            if (k >= Z) k -= Z;
+                            x[u] = act ? __ldcs(y + col * Z + k) : 0.0f;
                         }
+                    }
 #pragma unroll
-                        for (int u = 0; u < 16; u++) {
-                            const int col = c0 + u;
-                            if (col < C) { softn[col * CS] = x[u]; softn[col * CS + Z] = x[u]; }
+                    for (int u = 0; u < 16; u++) {
+                        const int col = c0 + u;
+                        if (col < C) {
+                            if (act) { softn[col * CS] = x[u]; softn[col * CS + Z] = x[u]; }
+                            const unsigned w = __ballot_sync(0xffffffffu, act && x[u] < 0.0f);   // the packed decisions of the
+                            if (lane0) hbw[col * HW] = w;                                         // channel values, as pack() builds them
                         }
                     }
                 }
+                packed = true;
             } else {
                 const double* y = (const double*)io.llr + (size_t)f * N;
                 if (ALL_ACTIVE || active) {
@@ -493,7 +498,7 @@ struct LmsTmem {
             tmem_wait_st();
             __syncthreads();
 
-            pack(soft2, hb, tid);
+            if (!packed) pack(soft2, hb, tid);
             int parity = syndrome(hb, plan, tid);                                   // :5111-5115
             int ret = 0, locked = 0, iter;
             if (!parity) { ret = 1; locked = 1; }
