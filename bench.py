@@ -93,7 +93,7 @@ def run_reference(args):
         return
     from oracle import pyoracle as po
     if not po.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libldpcref.so missing (build with make -C oracle ref)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libldpcref.so missing (build with make -C oracle ref)"})
         return
     cores = os.cpu_count() or 1
     frames_per_core = 200                       # ~1.5 s of CPU work per core per step at ~0.13 k frames/s/core
@@ -119,7 +119,7 @@ def run_reference(args):
                                        "lmin_sum_decod_qc_lm, error counting), one process per core" % frames_per_core},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -171,8 +171,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -327,7 +325,7 @@ def run_ours(args):
                           "thread_instr_peak_per_s": issue_peak, "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(dec, llr, hard, iters, K)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -369,7 +367,25 @@ def dec_hd(dec):
     return load_code(CODE)[0]
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # Libraries write to stdout behind our back (NCCL prints its version banner there when the first communicator is
+    # created): keep the real stdout for the result line and point fd 1 at stderr for everything else.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
