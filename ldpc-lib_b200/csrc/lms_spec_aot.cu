@@ -22,7 +22,7 @@ size_t lms_tmem_smem_bytes(int b, int c, int Z, int maxdeg)
     const int zp = (Z + 31) / 32 * 32, hw = zp / 32, nb = (Z + 31) / 32, nwarps = zp / 32;
     const size_t soft = 2 * (size_t)c * Z, hb = (size_t)(c * hw > 3 ? c * hw : 3) + 1;
     const size_t plan = (size_t)((b * nb + 8 * nwarps - 1) / (8 * nwarps)) * ((maxdeg + 3) / 4) * zp;
-    const size_t mbar = (soft + hb + plan + 1) & ~(size_t)1;
+    const size_t mbar = (soft + hb + plan + zp + 1) & ~(size_t)1;     // + the quick-look word per thread
     return sizeof(float) * (mbar + 2 + 4);
 }
 

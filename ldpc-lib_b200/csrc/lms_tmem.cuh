@@ -157,7 +157,8 @@ struct LmsTmem {
     static constexpr int HB_WORDS = (C * HW > 3 ? C * HW : 3) + 1;
     static constexpr int PLAN_OFF = SOFT_WORDS + HB_WORDS;
     static constexpr int PLAN_WORDS = ((B * NB + 8 * NWARPS - 1) / (8 * NWARPS)) * ((K::MAXDEG + 3) / 4) * ZP;
-    static constexpr int MBAR_OFF = (PLAN_OFF + PLAN_WORDS + 1) & ~1;
+    static constexpr int PLAN1_OFF = PLAN_OFF + PLAN_WORDS;      // quick syndrome look (syndrome_quick): one word per thread
+    static constexpr int MBAR_OFF = (PLAN1_OFF + ZP + 1) & ~1;
     static constexpr int MISC_OFF = MBAR_OFF + 2;
     static constexpr int SMEM_WORDS = MISC_OFF + 4;
 
@@ -342,24 +343,65 @@ struct LmsTmem {
                 plan[(r * SYN_QE + i) * ZP + tid] = pk;
             }
         }
+        {   // quick look: the first 2 * NWARPS tasks, 16 lanes each, one (task, edge) pair per lane
+            const int t = warp * 2 + (lane >> 4), q16 = lane & 15;
+            unsigned pk = (unsigned)(HB_WORDS - 1) | (32u << 25);
+            if (t < SYN_NT) {
+                const int j = t / NB, w = t - j * NB;
+                const int e = K::rt_rp()[j] + q16;
+                if (e < K::rt_rp()[j + 1]) {
+                    int start = 32 * w + K::rt_synsh()[e];
+                    if (start >= Z) start -= Z;
+                    const int i0 = start >> 5, i1 = i0 + 1 < HW ? i0 + 1 : (Z % 32 == 0 ? 0 : HW - 1);
+                    const int nvalid = Z - start < 32 ? Z - start : 32;
+                    pk = (unsigned)(K::rt_col()[e] * HW) | ((unsigned)i0 << 10) | ((unsigned)i1 << 15) | ((unsigned)(start & 31) << 20)
+                         | ((unsigned)nvalid << 25);
+                }
+            }
+            plan[PLAN_WORDS + tid] = pk;
+        }
+    }
+
+    static __device__ __forceinline__ unsigned window(const unsigned* hb, unsigned pk)
+    {
+        const unsigned* hc = hb + (pk & 1023u);
+        unsigned win = __funnelshift_r(hc[(pk >> 10) & 31u], hc[(pk >> 15) & 31u], pk >> 20);     // shift uses the low 5 bits
+        if constexpr (Z % 32 != 0) {
+            const unsigned nvalid = (pk >> 25) & 63u;       // the window runs over the end of the column: the rest wraps to bit 0
+            if (nvalid < 32u) win = (win & ((1u << nvalid) - 1u)) | (hc[0] << nvalid);
+        }
+        return win;
+    }
+
+    // A cheap look at the first 2 * NWARPS tasks (a sixteenth to an eighth of the check rows): before a frame has
+    // converged nearly every look finds an unsatisfied check and the full pass is skipped.  The verdict "non-zero" is
+    // exact; "zero" only means that syndrome() has to decide.
+    static constexpr bool SYN_QUICK = K::MAXDEG <= 16 && SYN_NT > 2 * NWARPS;
+    static __device__ __forceinline__ int syndrome_quick(const unsigned* hb, const unsigned* plan, int tid)
+    {
+        unsigned acc = window(hb, plan[PLAN_WORDS + tid]);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+        if constexpr (Z % 32 != 0) {
+            const int t = (tid >> 5) * 2 + ((tid & 31) >> 4);
+            const int lanes = Z - 32 * (t % NB);
+            if (lanes < 32) acc &= (1u << lanes) - 1u;
+        }
+        return __syncthreads_or(acc != 0);
     }
 
     static __device__ __forceinline__ int syndrome(const unsigned* hb, const unsigned* plan, int tid)
     {
+        if constexpr (SYN_QUICK) {
+            if (syndrome_quick(hb, plan, tid)) return 1;
+        }
         unsigned bad = 0;
 #pragma unroll
         for (int r = 0; r < SYN_ROUNDS; r++) {
             unsigned acc = 0;
 #pragma unroll
             for (int i = 0; i < SYN_QE; i++) {
-                const unsigned pk = plan[(r * SYN_QE + i) * ZP + tid];
-                const unsigned* hc = hb + (pk & 1023u);
-                unsigned win = __funnelshift_r(hc[(pk >> 10) & 31u], hc[(pk >> 15) & 31u], pk >> 20);     // shift uses the low 5 bits
-                if constexpr (Z % 32 != 0) {
-                    const unsigned nvalid = (pk >> 25) & 63u;       // the window runs over the end of the column: the rest wraps to bit 0
-                    if (nvalid < 32u) win = (win & ((1u << nvalid) - 1u)) | (hc[0] << nvalid);
-                }
-                acc ^= win;
+                acc ^= window(hb, plan[(r * SYN_QE + i) * ZP + tid]);
             }
             acc ^= __shfl_xor_sync(0xffffffffu, acc, 1);
             acc ^= __shfl_xor_sync(0xffffffffu, acc, 2);
