@@ -25,7 +25,7 @@
 // 1/2 LOP3 (sign parity), FSETP + SEL + LOP3 (new message) -- about half the instructions of lms_spec.cuh.
 //
 // Generated `Code` (tools/gen_lms_spec.py kind "lmst", spec_jit.cpp variant 2) adds to the lms_spec fields:
-//   static constexpr int DELTA[E], ROT[C], RI[C], SYNSH[E], TCOLS;  rt_rot() / rt_ri() / rt_synsh() __constant__ copies.
+//   static constexpr int DELTA[E], ROT[C], RI[C], SYNSH[E], TCOLS; bool LAST[E], EARLY[E];  rt_rot() / rt_ri() / rt_synsh() __constant__ copies.
 // This header must stay free of #include (NVRTC compiles it as one string after lms_spec.cuh).
 #pragma once
 
@@ -162,14 +162,32 @@ struct LmsTmem {
     static constexpr int MISC_OFF = MBAR_OFF + 2;
     static constexpr int SMEM_WORDS = MISC_OFF + 4;
 
+    // Edge Q of block row J reads a column that block row J - 1 does not write: its value is final once the barrier
+    // before block row J - 1 has passed, so the load can be issued one block row early (and its latency hidden behind
+    // that row's arithmetic and barrier) -- prefetch() below.  Block row 0 follows the syndrome check: nothing early.
+    // K::EARLY[e] (generated) says so; NDEG<J> = weight of block row J (1 for J = B, the array that is never used).
+    template <int J> static constexpr int NDEG = J < B ? K::RP[(J < B ? J : 0) + 1] - K::RP[J < B ? J : 0] : 1;
+
     template <int J, int Q>
-    static __device__ __forceinline__ void load_soft(const float* softn, float (&sv)[K::RP[J + 1] - K::RP[J]])
+    static __device__ __forceinline__ void load_soft(const float* softn, float (&sv)[K::RP[J + 1] - K::RP[J]], const float (&pre)[NDEG<J>])
     {
         constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
         if constexpr (Q < DEG) {
             constexpr int off = K::COL[E0 + Q] * CS + K::DELTA[E0 + Q];
-            sv[Q] = softn[off];
-            load_soft<J, Q + 1>(softn, sv);
+            if constexpr (K::EARLY[E0 + Q]) sv[Q] = pre[Q];
+            else sv[Q] = softn[off];
+            load_soft<J, Q + 1>(softn, sv, pre);
+        }
+    }
+    template <int JN, int Q>
+    static __device__ __forceinline__ void prefetch(const float* softn, float (&nxt)[NDEG<JN>])
+    {
+        if constexpr (JN < B) {
+            if constexpr (Q < K::RP[JN + 1] - K::RP[JN]) {
+                constexpr int off = K::COL[K::RP[JN] + Q] * CS + K::DELTA[K::RP[JN] + Q];
+                if constexpr (K::EARLY[K::RP[JN] + Q]) nxt[Q] = softn[off];
+                prefetch<JN, Q + 1>(softn, nxt);
+            }
         }
     }
 
@@ -262,13 +280,15 @@ struct LmsTmem {
     }
 
     template <int J>
-    static __device__ __forceinline__ void layer(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active)
+    static __device__ __forceinline__ void layer(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active,
+                                                 const float (&pre)[NDEG<J>], float (&nxt)[NDEG<J + 1>])
     {
         constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
         unsigned msg[DEG];
         float sv[DEG], v[DEG];
         tmem_ld_n<DEG>(trow + E0, msg);                                                          // old c2v of this row
-        load_soft<J, 0>(softn, sv);
+        load_soft<J, 0>(softn, sv, pre);
+        prefetch<J + 1, 0>(softn, nxt);                                                          // the next block row's untouched columns
         tmem_wait_ld<DEG>(msg);
 #pragma unroll
         for (int q = 0; q + 1 < DEG; q += 2)                                                     // :5152-5158, two edges per FADD2
@@ -288,12 +308,14 @@ struct LmsTmem {
     }
 
     template <int J>
-    static __device__ __forceinline__ void layers(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active)
+    static __device__ __forceinline__ void layers(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active,
+                                                  const float (&pre)[NDEG<J>])
     {
         if constexpr (J < B) {
-            layer<J>(softn, hbw, trow, mbar, ph, lane0, active);
+            float nxt[NDEG<J + 1>];
+            layer<J>(softn, hbw, trow, mbar, ph, lane0, active, pre, nxt);
             __syncthreads();
-            layers<J + 1>(softn, hbw, trow, mbar, ph, lane0, active);
+            layers<J + 1>(softn, hbw, trow, mbar, ph, lane0, active, nxt);
         }
     }
 
@@ -547,7 +569,7 @@ struct LmsTmem {
             for (iter = 0; iter < io.maxiter; iter++) {
                 if (!parity && !noexit) break;                                          // :5119
                 tmem_wait_st();                                                         // last iteration's messages are in place
-                layers<0>(softn, hbw, trow, mbar, ph, lane0, active);
+                { float none[NDEG<0>]; layers<0>(softn, hbw, trow, mbar, ph, lane0, active, none); }
                 if (locked) continue;                                                   // fixed-iteration mode after the first success: the verdict is known
                 parity = syndrome(hb, plan, tid);                                   // :5281-5284
                 if (!parity && !locked) { ret = iter + 1; locked = 1; }

@@ -116,6 +116,16 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
     put_array(o, "    static constexpr int RI", ri, g.c);
     put_array(o, "    static constexpr int SYNSH", synsh, g.E);
     put_array(o, "    static constexpr bool LAST", lastw, g.E);
+    {   // column untouched by the previous block row: its value can be loaded one block row ahead (lms_tmem.cuh prefetch)
+        std::vector<int> early(g.E, 0);
+        for (int j = 1; j < g.b; j++)
+            for (int e = g.rp[j]; e < g.rp[j + 1]; e++) {
+                bool hit = false;
+                for (int e2 = g.rp[j - 1]; e2 < g.rp[j]; e2++) hit |= g.col[e2] == g.col[e];
+                early[e] = !hit;
+            }
+        put_array(o, "    static constexpr bool EARLY", early, g.E);
+    }
     o << "    static __device__ __forceinline__ const int* rt_rot() { return RT_ROT; }\n";
     o << "    static __device__ __forceinline__ const int* rt_ri() { return RT_RI; }\n";
     o << "    static __device__ __forceinline__ const int* rt_synsh() { return RT_SYNSH; }\n";

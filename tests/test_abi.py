@@ -152,6 +152,7 @@ def test_runtime_generator_emits_the_same_tensor_memory_tables_as_the_build_time
         rot, delta, ri, synsh, tcols, lastw = gen.tmem_tables(b, c, Z, rp, col, sh, zp)
         assert arr("DELTA") == delta and arr("ROT") == rot and arr("RI") == ri and arr("SYNSH") == synsh and arr("LAST") == lastw
         assert int(re.search(r"TCOLS = (\d+)", txt).group(1)) == tcols
+        assert arr("EARLY") == gen.early_table(b, rp, col)
         # one pass over the edges in schedule order: a column read at n + DELTA and rewritten lane-aligned ends rotated by ROT
         cur = list(rot)
         for e in range(len(col)):

@@ -49,6 +49,17 @@ def tmem_tables(b, c, Z, rp, col, sh, zp):
     return rot, delta, ri, synsh, tcols, lastw
 
 
+def early_table(b, rp, col):
+    """EARLY[e]: the column of edge e (block row j >= 1) is not touched by block row j - 1, so its value can be loaded one
+    block row ahead (lms_tmem.cuh prefetch)."""
+    early = []
+    for j in range(b):
+        prev = set(col[rp[j - 1]:rp[j]]) if j > 0 else None
+        for e in range(rp[j], rp[j + 1]):
+            early.append(1 if (j > 0 and col[e] not in prev) else 0)
+    return early
+
+
 def emit(name, hd, Z, minb, kind="lms"):
     b, c = hd.shape
     rp, col, sh = [0], [], []
@@ -89,6 +100,7 @@ def emit(name, hd, Z, minb, kind="lms"):
     out.append("    static constexpr int RI[%d] = %s;" % (c, arr(ri)))
     out.append("    static constexpr int SYNSH[%d] = %s;" % (E, arr(synsh)))
     out.append("    static constexpr bool LAST[%d] = %s;      // last edge of its block column (ascending block rows)" % (E, arr(lastw)))
+    out.append("    static constexpr bool EARLY[%d] = %s;     // column untouched by the previous block row" % (E, arr(early_table(b, rp, col))))
     out.append("    static __device__ __forceinline__ const int* rt_rot() { return RT_ROT; }")
     out.append("    static __device__ __forceinline__ const int* rt_ri() { return RT_RI; }")
     out.append("    static __device__ __forceinline__ const int* rt_synsh() { return RT_SYNSH; }")
