@@ -41,10 +41,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CODE, Z, SNR_DB, MAXITER, DECODER = "ref32x16_b", 256, 2.0, 10, 8      # 8 = LMS_DEC
 FRAMES_PER_GPU = 1 << 20
 METRIC, UNIT = "decoded_info_gbps_10iter", "Gbit/s"
-TRAFFIC_BYTES_PER_FRAME = (2149576000 + 15778304) / 65536        # ncu capture of the bench kernel (lmst_spec_c2t): 33 041 B per frame
+TRAFFIC_BYTES_PER_FRAME = (2148866000 + 16032256) / 65536        # ncu capture of the bench kernel (lmst_spec_c2t): 33 034 B per frame
 # SASS instruction mix of one iteration of the bench kernel (tools/sass_mix.py on the built object; profiles/):
 # (ALU-pipe, total) instructions per edge update and lane
-SASS_MIX = {True: (6.94, 12.84, "lms_tmem (profiles/r01_lms_tmem_v6_ncu.txt, tools/sass_mix.py)"),
+SASS_MIX = {True: (6.94, 12.84, "lms_tmem (profiles/r01_lms_tmem_v7_ncu.txt, tools/sass_mix.py)"),
             False: (13.9, 25.6, "lms_spec (profiles/r01_lms_spec_v1_ncu.txt)")}
 
 
@@ -313,7 +313,7 @@ def run_ours(args):
                                            "call": "ldpcb200_simulate, reference semantics (max 10 iterations, syndrome early exit)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": TRAFFIC_BYTES_PER_FRAME * frames, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame,
-                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_tmem_v6_ncu.txt (ncu --set full, "
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_tmem_v7_ncu.txt (ncu --set full, "
                                                "65536 frames) scaled to this launch"},
                 # the binding roofline: min-sum is compare / select / logic work that issues on the
                 # ALU pipe (64 lanes / clk / SM); ALU-pipe and total SASS instructions per edge update of the kernel
