@@ -21,8 +21,9 @@
 //    edge); at iteration boundaries column k is rotated by the shift of its last block row (K::ROT), which
 //    the frame load, the syndrome windows (K::SYNSH) and the outputs take into account (K::RI = (Z - ROT) mod Z).
 //
-// Per edge-update this leaves: 1 LDS + 2 STS, 2 FADD, ~2 FMNMX (two-smallest tracking, two edges per step),
-// 1/2 LOP3 (sign parity), FSETP + SEL + LOP3 (new message) -- about half the instructions of lms_spec.cuh.
+// Per edge-update this leaves: 1 LDS + 2 STS, one FADD2 (two edges per instruction), ~2.7 FMNMX (two smallest of the row
+// through a balanced tree + the offset / clamp per row), 1/2 LOP3 (sign parity), FSETP + SEL + LOP3 (new message),
+// 0.6 LDTM / STTM: 12.8 SASS instructions, 6.9 of them on the ALU pipe (tools/sass_mix.py) -- half of lms_spec.cuh.
 //
 // Generated `Code` (tools/gen_lms_spec.py kind "lmst", spec_jit.cpp variant 2) adds to the lms_spec fields:
 //   static constexpr int DELTA[E], ROT[C], RI[C], SYNSH[E], TCOLS; bool LAST[E], EARLY[E];  rt_rot() / rt_ri() / rt_synsh() __constant__ copies.

@@ -1,18 +1,24 @@
-// TASP_DEC throughput kernel (layered sum-product in the probability domain, decoders.cpp:2584-2744), double like the
-// reference and in the reference's operation order -- the same expressions as TaspGeneric (dec_sumprod.cu), so results
-// are the parity kernel's bit for bit.  Table-driven (any code, no compilation step: this is also the kernel the
-// code-search caller gets), one frame per CTA at a time, persistent grid, lane n = check row n of every block row.
+// Throughput kernels of the sum-product family with the messages in TENSOR MEMORY -- table-driven (any code, no
+// compilation step: these are also the kernels the code-search caller gets), one frame per CTA at a time, persistent
+// grid, lane n = check row n of every block row:
 //
-// What makes it faster than the parity kernel (which keeps everything in an L2-resident workspace and its per-row
-// arrays in local memory because the row weight is a run-time value):
-//   * lambda messages (Z[row][edge], decoders.cpp:2620-2641) in TENSOR MEMORY: two 32-bit TMEM columns per edge and
-//     lane, fetched / put back per block row with one tcgen05.ld / tcgen05.st group (run-time column address);
-//   * posteriors gamma (N doubles) in shared memory;
-//   * the block row is processed by a function templated on the row weight (switch dispatch), so rho[], the
-//     forward / backward products of map_bin and the new messages live in registers;
-//   * edge tables (bit offset, shift) in shared memory.
-// Codes whose messages do not fit the 512 TMEM columns (2 * E * ceil(threads / 128) > 512) or whose row weight exceeds
-// TASP_MAXDEG stay on the parity kernel.
+//   tasp_fast_kernel<.., false>  TASP_DEC  tdmp_sum_prod_gf2_decod_qc_lm   decoders.cpp:2584-2744   layered, probability domain, double
+//   tasp_fast_kernel<.., true>   LCHE_DEC  lche_decod                      decoders.cpp:2893-3010   layered, LLR domain + look-up tables, double
+//   asp_fast_kernel              ASP_DEC   sum_prod_gf2_decod_qc_lm        decoders.cpp:2324-2581   flooding, probability domain, double
+//   iasp_fast_kernel             IASP_DEC  isum_prod_gf2_decod_qc_lm       decoders.cpp:3822-4121   flooding, 12-bit fixed point
+//
+// All in the reference's arithmetic and operation order (the expressions of the parity kernels in dec_sumprod.cu, which
+// they equal bit for bit: tests/test_gpu_tmem.py).  What makes them faster than the parity kernels (which keep
+// everything in an L2-resident workspace and their per-row arrays in local memory because the row weight is a run-time
+// value):
+//   * messages in TMEM: two 32-bit columns per edge and lane for the double decoders, one for IASP_DEC, fetched / put
+//     back with one tcgen05.ld / tcgen05.st group per block row or per four edges (run-time column address);
+//   * posteriors / per-bit products in shared memory, edge tables (bit offset, shift) in shared memory;
+//   * block rows processed by functions templated on the row weight (switch dispatch), so rho[], the forward /
+//     backward products of map_bin and the new messages live in registers; passes without row structure are flat
+//     loops over the edges (small code: the CTAs of an SM sit at different places of the kernel);
+//   * double divisions through div_normal (channel.cuh): correctly rounded, no slow-path branch.
+// Codes whose messages do not fit the 512 TMEM columns or whose row weight exceeds TASP_MAXDEG stay on the parity kernels.
 #include "dec_common.cuh"
 #include "lms_spec.cuh"
 #include "lms_tmem.cuh"
