@@ -2,8 +2,9 @@
 // compilation step: these are also the kernels the code-search caller gets), one frame per CTA at a time, persistent
 // grid, lane n = check row n of every block row:
 //
-//   tasp_fast_kernel<.., false>  TASP_DEC  tdmp_sum_prod_gf2_decod_qc_lm   decoders.cpp:2584-2744   layered, probability domain, double
-//   tasp_fast_kernel<.., true>   LCHE_DEC  lche_decod                      decoders.cpp:2893-3010   layered, LLR domain + look-up tables, double
+//   tasp_fast_kernel<.., 0>      TASP_DEC  tdmp_sum_prod_gf2_decod_qc_lm   decoders.cpp:2584-2744   layered, probability domain, double
+//   tasp_fast_kernel<.., 1>      LCHE_DEC  lche_decod                      decoders.cpp:2893-3010   layered, LLR domain + look-up tables, double
+//   tasp_fast_kernel<.., 2>      LMS_DEC   lmin_sum_decod_qc_lm            decoders.cpp:5064-5425   layered offset min-sum in DOUBLE (bit-exact posteriors)
 //   asp_fast_kernel              ASP_DEC   sum_prod_gf2_decod_qc_lm        decoders.cpp:2324-2581   flooding, probability domain, double
 //   iasp_fast_kernel             IASP_DEC  isum_prod_gf2_decod_qc_lm       decoders.cpp:3822-4121   flooding, 12-bit fixed point
 //
@@ -182,18 +183,67 @@ __device__ __forceinline__ void lf_row(double* so, const double* tab, const unsi
     tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
 }
 
-template <int RW, bool LCHE>
+// ---- LMS_DEC in double (lmin_sum_decod_qc_lm, decoders.cpp:5064-5425): the reference's own arithmetic, for callers that
+// want its posteriors bit for bit (LDPCB200_PRECISION=64; the fp32 kernels of lms_tmem.cuh agree on decisions and
+// iteration counts but round their posteriors to fp32).  Same skeleton: c2v messages explicit in TMEM (two columns per
+// edge and lane -- the reference's compressed prev[] {min1, min2, pos, sign} + signs[] reconstruct exactly these
+// values, :5152-5158), posteriors in shared memory.  The offset max(|v2c| - 0.4, 0) and the 32767 ceiling are monotone,
+// so they are applied to the two smallest |v2c| instead of to every edge; "position of the first minimum" is replaced by
+// "magnitude equals the minimum" (ties select equal values).
+template <int RW>
+__device__ __forceinline__ void lm_row(double* so, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    unsigned lw[2 * RW];
+    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    int idx[RW];
+    double x[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)(pk >> 16);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        x[q] = so[idx[q]];
+    }
+    tmem_wait_ld<2 * RW>(lw);
+    double v[RW], u[RW];
+    int csign = 0;
+    double c1 = __longlong_as_double(0x7ff0000000000000ll), c2 = c1;
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        v[q] = x[q] - __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);    // :5158
+        csign ^= v[q] < 0;
+        u[q] = v[q] < 0.0 ? -v[q] : v[q];
+        if (u[q] < c1) { c2 = c1; c1 = u[q]; }                                   // process_check_node :5012-5027 on the raw magnitudes
+        else if (u[q] < c2) c2 = u[q];
+    }
+    double n1 = c1 - 0.4, n2 = c2 - 0.4;                                          // :5166-5168, ceiling MAX_VAL :5131-5137
+    n1 = n1 < 0 ? 0.0 : n1; n2 = n2 < 0 ? 0.0 : n2;
+    n1 = n1 < 32767.0 ? n1 : 32767.0; n2 = n2 < 32767.0 ? n2 : 32767.0;
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double cabs = u[q] == c1 ? n2 : n1;                                // :5193
+        const double cval = ((v[q] < 0) ^ csign) ? -cabs : cabs;                 // :5194-5198
+        if (active) so[idx[q]] = v[q] + cval;                                    // :5199-5204
+        lw[2 * q] = (unsigned)__double2loint(cval);
+        lw[2 * q + 1] = (unsigned)__double2hiint(cval);
+    }
+    tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+}
+
+template <int RW, int FL>
 __device__ __noinline__ void tf_row_call(double* gam, const double* tab, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
 {
-    if constexpr (LCHE) lf_row<RW>(gam, tab, etab, e0, n, Z, active, trow);
+    if constexpr (FL == 2) lm_row<RW>(gam, etab, e0, n, Z, active, trow);
+    else if constexpr (FL == 1) lf_row<RW>(gam, tab, etab, e0, n, Z, active, trow);
     else tf_row<RW>(gam, etab, e0, n, Z, active, trow);
 }
 
-template <bool LCHE>
+template <int FL>
 __device__ __forceinline__ void tf_dispatch(int cnt, double* gam, const double* tab, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
 {
     switch (cnt) {
-#define TF_CASE(k) case k: tf_row_call<k, LCHE>(gam, tab, etab, e0, n, Z, active, trow); break;
+#define TF_CASE(k) case k: tf_row_call<k, FL>(gam, tab, etab, e0, n, Z, active, trow); break;
     TF_CASE(2) TF_CASE(3) TF_CASE(4) TF_CASE(5) TF_CASE(6) TF_CASE(7) TF_CASE(8) TF_CASE(9) TF_CASE(10) TF_CASE(11)
     TF_CASE(12) TF_CASE(13) TF_CASE(14) TF_CASE(15) TF_CASE(16) TF_CASE(17) TF_CASE(18) TF_CASE(19) TF_CASE(20)
 #undef TF_CASE
@@ -222,7 +272,8 @@ __device__ __forceinline__ int tf_syndrome(const double* gam, const unsigned* et
     return __syncthreads_or(bad);
 }
 
-template <int MAXT, bool LCHE>
+// FL: 0 TASP_DEC, 1 LCHE_DEC, 2 LMS_DEC in double
+template <int MAXT, int FL>
 __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
 {
     extern __shared__ __align__(16) double tf_smem[];
@@ -254,33 +305,33 @@ __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, con
     for (;;) {
         const int f = next_frame(io);
         if (f >= io.nf) break;
-        for (int i = tid; i < N; i += nt) gam[i] = LCHE ? load_llr(io, N, f, i) : tf_llr_to_p1(load_llr(io, N, f, i));   // :2611-2646 / :2916
+        for (int i = tid; i < N; i += nt) gam[i] = FL ? load_llr(io, N, f, i) : tf_llr_to_p1(load_llr(io, N, f, i));   // :2611-2646 / :2916 / :5088
         {   // TASP: lambda = 0.5 for every edge (:2620-2641), 0x3FE0000000000000; LCHE: st = 0 (:2913-2915)
-            unsigned half[2] = { 0u, LCHE ? 0u : 0x3FE00000u };
+            unsigned half[2] = { 0u, FL ? 0u : 0x3FE00000u };
             for (int e = 0; e < E; e++) TmemRow<2>::st(trow + 2u * (unsigned)e, half);
             tmem_wait_st();
         }
         __syncthreads();
-        int synd = tf_syndrome<LCHE>(gam, etab, rpw, b, Z, n, active);                           // :2653 / :2927-2931
+        int synd = tf_syndrome<FL != 0>(gam, etab, rpw, b, Z, n, active);                        // :2653 / :2927-2931 / :5111-5115
         int ret = 0, locked = 0, steps = 0;
-        if (!synd) { locked = 1; ret = 0; }                                                      // :2654-2660
+        if (!synd) { locked = 1; ret = FL == 2 ? 1 : 0; }                                        // :2654-2660; LMS_DEC: 0 + 1 (:5424)
         if (synd || noexit) {
             while (steps < io.maxiter) {
                 tmem_wait_st();
                 for (int j = 0; j < b; j++) {
                     const int e0 = rpw[j];
-                    tf_dispatch<LCHE>(rpw[j + 1] - e0, gam, tab, etab, e0, n, Z, active, trow);
+                    tf_dispatch<FL>(rpw[j + 1] - e0, gam, tab, etab, e0, n, Z, active, trow);
                     __syncthreads();
                 }
                 // the reference re-checks after every layer (:2723); only the last verdict is used (:2733)
-                synd = tf_syndrome<LCHE>(gam, etab, rpw, b, Z, n, active);
+                synd = tf_syndrome<FL != 0>(gam, etab, rpw, b, Z, n, active);
                 steps++;
                 if (!synd) { if (!locked) { ret = steps; locked = 1; } if (!noexit) break; }
             }
         }
         if (!locked) ret = synd ? -steps : steps;                                                // :2740-2743
         for (int i = tid; i < N; i += nt) store_post(io, N, f, i, gam[i]);
-        emit_frame(g, io, f, ret, [&](int i) { return LCHE ? (int)(gam[i] < 0.0) : (int)(gam[i] > 0.5); });   // :2738 / :3003
+        emit_frame(g, io, f, ret, [&](int i) { return FL ? (int)(gam[i] < 0.0) : (int)(gam[i] > 0.5); });   // :2738 / :3003 / :5421
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -688,7 +739,7 @@ __global__ void __launch_bounds__(MAXT, MINB) iasp_fast_kernel(const TaspTab T, 
 
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
-// decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC, LDPCB200_ASP_DEC or LDPCB200_IASP_DEC
+// decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC, LDPCB200_ASP_DEC, LDPCB200_IASP_DEC or LDPCB200_LMS_DEC (double)
 FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block)
 {
     FastPlan p;
@@ -730,10 +781,12 @@ cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, 
         kern = p.threads <= 128 ? iasp_fast_kernel<128, 4> : p.threads <= 256 ? iasp_fast_kernel<256, 2> : p.threads <= 512 ? iasp_fast_kernel<512, 1> : iasp_fast_kernel<1024, 1>;   // <= 128 registers
     else if (decoder_id == LDPCB200_ASP_DEC)
         kern = p.threads <= 128 ? asp_fast_kernel<128> : p.threads <= 256 ? asp_fast_kernel<256> : p.threads <= 512 ? asp_fast_kernel<512> : asp_fast_kernel<1024>;
+    else if (decoder_id == LDPCB200_LMS_DEC)
+        kern = p.threads <= 128 ? tasp_fast_kernel<128, 2> : p.threads <= 256 ? tasp_fast_kernel<256, 2> : p.threads <= 512 ? tasp_fast_kernel<512, 2> : tasp_fast_kernel<1024, 2>;
     else if (decoder_id == LDPCB200_LCHE_DEC)
-        kern = p.threads <= 128 ? tasp_fast_kernel<128, true> : p.threads <= 256 ? tasp_fast_kernel<256, true> : p.threads <= 512 ? tasp_fast_kernel<512, true> : tasp_fast_kernel<1024, true>;
+        kern = p.threads <= 128 ? tasp_fast_kernel<128, 1> : p.threads <= 256 ? tasp_fast_kernel<256, 1> : p.threads <= 512 ? tasp_fast_kernel<512, 1> : tasp_fast_kernel<1024, 1>;
     else
-        kern = p.threads <= 128 ? tasp_fast_kernel<128, false> : p.threads <= 256 ? tasp_fast_kernel<256, false> : p.threads <= 512 ? tasp_fast_kernel<512, false> : tasp_fast_kernel<1024, false>;
+        kern = p.threads <= 128 ? tasp_fast_kernel<128, 0> : p.threads <= 256 ? tasp_fast_kernel<256, 0> : p.threads <= 512 ? tasp_fast_kernel<512, 0> : tasp_fast_kernel<1024, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, p.threads, p.smem_bytes, s>>>(T, g, io);
