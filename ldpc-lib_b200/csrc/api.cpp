@@ -157,9 +157,9 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
         h->last_launches++;
     }
     bool use_fast = h->fast.ok && !(io.post && io.post_dtype != default_post_dtype(h->decoder_id, h->p.precision));
-    if (use_fast && h->decoder_id == LDPCB200_LMS_DEC && h->p.precision == 64) {
+    if (use_fast && (h->decoder_id == LDPCB200_LMS_DEC || h->decoder_id == LDPCB200_MS_DEC) && h->p.precision == 64) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
-        CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream));
+        CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream, h->dp.alpha));
     } else if (use_fast && h->decoder_id == LDPCB200_LMS_DEC) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);
         CU(launch_lms_fast(h->fast, io, std::max(fgrid, 1), h->stream));
@@ -316,6 +316,7 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
             if (decoder_id == LDPCB200_LMS_DEC && p.precision == 64) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);   // double: tasp_fast.cu
             else if (decoder_id == LDPCB200_LMS_DEC) h->fast = plan_lms_fast(h->g, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2);
             else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ms_fast(h->g, 2, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
+            else if (decoder_id == LDPCB200_MS_DEC && p.precision == 64) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);    // double: tasp_fast.cu
             else if (decoder_id == LDPCB200_MS_DEC) h->fast = plan_ms_fast(h->g, 1, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
             else if (decoder_id == LDPCB200_TASP_DEC || decoder_id == LDPCB200_ASP_DEC || decoder_id == LDPCB200_LCHE_DEC || decoder_id == LDPCB200_IASP_DEC) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
         }

@@ -7,6 +7,7 @@
 //   tasp_fast_kernel<.., 2>      LMS_DEC   lmin_sum_decod_qc_lm            decoders.cpp:5064-5425   layered offset min-sum in DOUBLE (bit-exact posteriors)
 //   asp_fast_kernel              ASP_DEC   sum_prod_gf2_decod_qc_lm        decoders.cpp:2324-2581   flooding, probability domain, double
 //   iasp_fast_kernel             IASP_DEC  isum_prod_gf2_decod_qc_lm       decoders.cpp:3822-4121   flooding, 12-bit fixed point
+//   ms64_fast_kernel             MS_DEC    min_sum_decod_qc_lm             decoders.cpp:4554-4767   flooding normalised min-sum in DOUBLE
 //
 // All in the reference's arithmetic and operation order (the expressions of the parity kernels in dec_sumprod.cu, which
 // they equal bit for bit: tests/test_gpu_tmem.py).  What makes them faster than the parity kernels (which keep
@@ -737,25 +738,178 @@ __global__ void __launch_bounds__(MAXT, MINB) iasp_fast_kernel(const TaspTab T, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// MS_DEC in double (min_sum_decod_qc_lm, decoders.cpp:4554-4767): flooding normalised min-sum in the reference's own
+// arithmetic (LDPCB200_PRECISION=64).  The sweeps of ms_tmem.cuh on this file's table-driven skeleton: messages (+-min,
+// unscaled: what the reference's STATE 1 adds, :4649-4658) are two TMEM columns per edge and lane;
+//   A  block row by block row (barrier in between): acc[bit] += message -- every bit sees its messages in ascending
+//      block-row order starting from 0, as :4633-4658 does;
+//   B  per bit: soft = y + acc * alpha (:4682);
+//   C  per check row, no barriers: v2c = soft - message * alpha, syndrome of this pass's decisions, the two smallest
+//      |v2c| (ceiling 32767 applied to them instead of to every edge, :4730), new messages (:4688-4755).
+template <int RW>
+__device__ __noinline__ void m6_rowA(double* A, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    unsigned lw[2 * RW];
+    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    int idx[RW];
+    double acc[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];                                        // bit offset | shift << 16 | first-of-column << 31
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        acc[q] = (pk >> 31) ? 0.0 : A[idx[q]];                                   // :4633
+    }
+    tmem_wait_ld<2 * RW>(lw);
+#pragma unroll
+    for (int q = 0; q < RW; q++)
+        if (active) A[idx[q]] = acc[q] + __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);   // :4658
+}
+
+template <int RW>
+__device__ __noinline__ int m6_rowC(const double* A, const unsigned* etab, int e0, int n, int Z, double alpha, unsigned trow)
+{
+    unsigned lw[2 * RW];
+    tmem_ld_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    double rs[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        rs[q] = A[(int)(pk & 0xffffu) + k];
+    }
+    tmem_wait_ld<2 * RW>(lw);
+    double tt[RW], u[RW];
+    int synd = 0, csign = 0;
+    double c1 = __longlong_as_double(0x7ff0000000000000ll), c2 = c1;
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        synd ^= rs[q] < 0;                                                       // :4711
+        tt[q] = rs[q] - __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]) * alpha;   // :4714-4722
+        csign ^= tt[q] < 0;
+        u[q] = tt[q] < 0.0 ? -tt[q] : tt[q];                                     // :4729
+        if (u[q] < c1) { c2 = c1; c1 = u[q]; }                                   // :4732-4746 on the raw magnitudes
+        else if (u[q] < c2) c2 = u[q];
+    }
+    const double n1 = c1 > 32767.0 ? 32767.0 : c1, n2 = c2 > 32767.0 ? 32767.0 : c2;     // :4730, init :4692-4696
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double cabs = u[q] == c1 ? n2 : n1;                                // :4649 (position of the minimum -> equality, ties select equal values)
+        const double cval = ((tt[q] < 0) ^ csign) ? -cabs : cabs;
+        lw[2 * q] = (unsigned)__double2loint(cval);
+        lw[2 * q + 1] = (unsigned)__double2hiint(cval);
+    }
+    tmem_st_n<2 * RW>(trow + 2u * (unsigned)e0, lw);
+    return synd;
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) ms64_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io, const double alpha)
+{
+    extern __shared__ __align__(16) double tf_smem[];
+    const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
+    double* A = tf_smem;                 // accumulator, then the posterior soft
+    double* y = A + N;                   // channel values
+    unsigned* etab = (unsigned*)(y + N);
+    int* rpw = (int*)(etab + E);
+    unsigned* s_t = (unsigned*)(rpw + b + 1);
+    const bool active = tid < Z;
+    const int n = active ? tid : Z - 1;
+    const bool noexit = io.flags & LDPCB200_NO_EARLY_EXIT;
+
+    for (int e = tid; e < E; e += nt) {
+        const int c = g.col[e];
+        etab[e] = (unsigned)(c * Z) | ((unsigned)g.sh[e] << 16) | (g.cedge[g.cp[c]] == e ? 0x80000000u : 0u);
+    }
+    for (int j = tid; j <= b; j += nt) rpw[j] = g.rp[j];
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(s_t)), "r"((unsigned)T.tcols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = *(volatile unsigned*)s_t;
+    const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * 2 * E), 0);
+
+    for (;;) {
+        const int f = next_frame(io);
+        if (f >= io.nf) break;
+        for (int i = tid; i < N; i += nt) { const double v = load_llr(io, N, f, i); y[i] = v; A[i] = v; }      // :4579-4596
+        {
+            unsigned zero[2] = { 0u, 0u };
+            for (int e = 0; e < E; e++) TmemRow<2>::st(trow + 2u * (unsigned)e, zero);
+            tmem_wait_st();
+        }
+        __syncthreads();
+        int parity = 1, ret = 0, locked = 0, iter;
+        for (iter = 0; iter < io.maxiter; iter++) {
+            for (int j = 0; j < b; j++) {                                                        // sweep A (STATE 1)
+                const int e0 = rpw[j];
+                switch (rpw[j + 1] - e0) {
+#define M6_A(k) case k: m6_rowA<k>(A, etab, e0, n, Z, active, trow); break;
+                case 1: m6_rowA<1>(A, etab, e0, n, Z, active, trow); break;
+                AF_CASES(M6_A)
+#undef M6_A
+                default: break;
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < N; i += nt) A[i] = y[i] + A[i] * alpha;                        // sweep B (STATE 2), :4682
+            __syncthreads();
+            int bad = 0;
+            for (int j = 0; j < b; j++) {                                                        // sweep C (STATE 3)
+                const int e0 = rpw[j];
+                switch (rpw[j + 1] - e0) {
+#define M6_C(k) case k: bad |= m6_rowC<k>(A, etab, e0, n, Z, alpha, trow); break;
+                case 1: bad |= m6_rowC<1>(A, etab, e0, n, Z, alpha, trow); break;
+                AF_CASES(M6_C)
+#undef M6_C
+                default: break;
+                }
+            }
+            tmem_wait_st();
+            parity = __syncthreads_or(active ? bad : 0);
+            if (!parity) { if (!locked) { ret = iter + 1; locked = 1; } if (!noexit) break; }    // :4761
+        }
+        if (!locked) ret = parity ? -iter : iter + 1;                                            // :4766
+        for (int i = tid; i < N; i += nt) store_post(io, N, f, i, A[i]);
+        emit_frame(g, io, f, ret, [&](int i) { return (int)(A[i] < 0); });
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)T.tcols) : "memory");
+    }
+}
+
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
-// decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC, LDPCB200_ASP_DEC, LDPCB200_IASP_DEC or LDPCB200_LMS_DEC (double)
+// decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC, LDPCB200_ASP_DEC, LDPCB200_IASP_DEC, or LDPCB200_LMS_DEC / LDPCB200_MS_DEC (double)
 FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block)
 {
     FastPlan p;
     const char* off = getenv("LDPCB200_NO_TASP_FAST");
     if (off && *off == '1') return p;
-    if (g.maxdeg > TASP_MAXDEG || g.mindeg < 2 || g.N > 65535 || g.Z > 1024) return p;   // (mindeg: map_bin; the row functions start at weight 2)
+    if (g.maxdeg > TASP_MAXDEG || g.N > 65535 || g.Z > 1024) return p;   // (row weight 1 only for MS_DEC: map_bin needs 2, the other row functions start at 2)
     const bool iasp = decoder_id == LDPCB200_IASP_DEC;
+    const bool ms = decoder_id == LDPCB200_MS_DEC;
     const bool asp = decoder_id == LDPCB200_ASP_DEC || iasp;
+    if (!ms && g.mindeg < 2) return p;
     if (asp && g.all_cw_2) { p.note = "all columns have weight 2: the reference's shortcut arithmetic stays on the parity kernel"; return p; }
-    for (int i = 0; asp && i < g.c; i++)
+    for (int i = 0; (asp || ms) && i < g.c; i++)
         if (g.cp[i + 1] == g.cp[i]) return p;                           // sweep R starts a bit's product at its first edge
     const int zp = (g.Z + 31) & ~31;
     int tcols = 32;
     while (tcols < (iasp ? 1 : 2) * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;        // fp64 messages take two columns, 12-bit ones one
     if (tcols > 512) { p.note = "the lambda messages (2 columns per edge) do not fit tensor memory"; return p; }
-    const size_t smem = (iasp ? sizeof(unsigned) * 3 * (size_t)g.N : sizeof(double) * ((size_t)g.N * (asp ? 3 : 1) + 96))
+    const size_t smem = (iasp ? sizeof(unsigned) * 3 * (size_t)g.N : sizeof(double) * ((size_t)g.N * (asp ? 3 : ms ? 2 : 1) + 96))
                         + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
     if (smem > (size_t)smem_per_block) return p;
     int m = 512 / tcols;
@@ -772,9 +926,17 @@ FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int sm
     return p;
 }
 
-cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s)
+cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s, double alpha)
 {
     const TaspTab& T = *reinterpret_cast<const TaspTab*>(p.tab.data());
+    if (decoder_id == LDPCB200_MS_DEC) {
+        void (*km)(const TaspTab, const QcDev, const FrameIO, const double) =
+            p.threads <= 128 ? ms64_fast_kernel<128> : p.threads <= 256 ? ms64_fast_kernel<256> : p.threads <= 512 ? ms64_fast_kernel<512> : ms64_fast_kernel<1024>;
+        cudaError_t e = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+        if (e != cudaSuccess) return e;
+        km<<<grid, p.threads, p.smem_bytes, s>>>(T, g, io, alpha);
+        return cudaGetLastError();
+    }
     // the register budget follows the CTA size: 255 registers per thread up to 256 threads
     void (*kern)(const TaspTab, const QcDev, const FrameIO);
     if (decoder_id == LDPCB200_IASP_DEC)

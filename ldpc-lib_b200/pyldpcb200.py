@@ -154,6 +154,8 @@ class Decoder:
             d["name"] = "tasp_fast_kernel<LCHE> (table-driven, double, messages in tensor memory)"
         if d["fast"] == 1 and self.decoder_id == LMS_DEC and self.precision == 64:
             d["name"] = "tasp_fast_kernel<LMS double> (table-driven, messages in tensor memory)"
+        if d["fast"] == 1 and self.decoder_id == MS_DEC and self.precision == 64:
+            d["name"] = "ms64_fast_kernel (table-driven, double, messages in tensor memory)"
         if d["fast"] == 1 and self.decoder_id == IASP_DEC:
             d["name"] = "iasp_fast_kernel (table-driven, 12-bit fixed point, messages in tensor memory)"
         if d["fast"] == 1 and self.decoder_id == ASP_DEC:

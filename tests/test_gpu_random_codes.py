@@ -52,7 +52,7 @@ def test_code_specialised_kernels_on_random_codes(ldpc, po, seed, dec, prec):
 
 
 @pytest.mark.parametrize("seed", SEEDS)
-@pytest.mark.parametrize("dec", ["TASP", "ASP", "LCHE", "IASP"])
+@pytest.mark.parametrize("dec", ["TASP", "ASP", "LCHE", "IASP", "MS"])
 def test_table_driven_tmem_kernels_on_random_codes(ldpc, po, seed, dec):
     hd, Z = random_code(seed)
     b, c = hd.shape
@@ -64,5 +64,5 @@ def test_table_driven_tmem_kernels_on_random_codes(ldpc, po, seed, dec):
         got = d.decode(llr, 8, want_post=True)
     bad = (got["iters"] != want["iters"]) | (got["hard"] != want["hard"]).any(axis=1)
     assert bad.sum() == 0, (info, hd.shape, Z, int(bad.sum()))
-    if dec in ("LCHE", "IASP"):
+    if dec in ("LCHE", "IASP", "MS"):
         assert np.array_equal(got["post"].astype(np.float64), want["post"].astype(np.float64))

@@ -41,7 +41,7 @@ def test_tmem_kernel_equals_register_kernel(ldpc, po, monkeypatch, dec, prec, co
     assert np.array_equal(fixed["iters"], a["iters"])                    # fixed-iteration mode reports the first success
 
 
-@pytest.mark.parametrize("dec", ["TASP", "ASP", "LCHE", "IASP", "LMS"])      # LMS: the double kernel on the same skeleton
+@pytest.mark.parametrize("dec", ["TASP", "ASP", "LCHE", "IASP", "LMS", "MS"])      # LMS, MS: the double kernels on the same skeleton
 def test_sumprod_fast_equals_parity_kernel(ldpc, po, monkeypatch, dec):
     did = getattr(po, dec)
     for code, Z, snr in [("ref32x16_b", 126, 2.0), ("c4_wifi_12x24", 81, 1.5), ("ref32x16_b", 256, 2.0)]:
