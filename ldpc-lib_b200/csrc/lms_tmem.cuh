@@ -29,6 +29,9 @@
 //   static constexpr int DELTA[E], ROT[C], RI[C], SYNSH[E], TCOLS; bool LAST[E], EARLY[E];  rt_rot() / rt_ri() / rt_synsh() __constant__ copies.
 // This header must stay free of #include (NVRTC compiles it as one string after lms_spec.cuh).
 #pragma once
+#ifndef LMS_TMEM_OTHERS
+#define LMS_TMEM_OTHERS 1
+#endif
 
 namespace ldpcb200 {
 
@@ -280,6 +283,61 @@ struct LmsTmem {
         }
     }
 
+    // m[q] = min(cap, min over p != q of |v[p]|): groups of three edges, one three-input minimum per edge
+    template <int DEG>
+    static __device__ __forceinline__ void min_of_others(const float (&v)[DEG], float (&m)[DEG], const float CAP)
+    {
+        constexpr int G = (DEG + 2) / 3;
+        float g[G], rest[G];
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const int a = 3 * k, b = a + 1 < DEG ? a + 1 : a, c = a + 2 < DEG ? a + 2 : a;
+            g[k] = fminf(fminf(fabsf(v[a]), fabsf(v[b])), fabsf(v[c]));
+        }
+        if constexpr (G == 1) rest[0] = CAP;
+        else if constexpr (G == 2) { rest[0] = fminf(g[1], CAP); rest[1] = fminf(g[0], CAP); }
+        else if constexpr (G == 3) {
+            rest[0] = fminf(fminf(g[1], g[2]), CAP); rest[1] = fminf(fminf(g[0], g[2]), CAP); rest[2] = fminf(fminf(g[0], g[1]), CAP);
+        } else {
+            float pre[G], suf[G];                                // minima of the groups before / after group k
+            pre[0] = CAP; suf[G - 2] = g[G - 1];
+#pragma unroll
+            for (int k = 1; k < G; k++) pre[k] = fminf(pre[k - 1], g[k - 1]);
+#pragma unroll
+            for (int k = G - 3; k >= 0; k--) suf[k] = fminf(suf[k + 1], g[k + 1]);
+#pragma unroll
+            for (int k = 0; k < G - 1; k++) rest[k] = fminf(pre[k], suf[k]);
+            rest[G - 1] = pre[G - 1];
+        }
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const int a = 3 * k;
+            if (a + 2 < DEG) {
+                m[a] = fminf(fminf(fabsf(v[a + 1]), fabsf(v[a + 2])), rest[k]);
+                m[a + 1] = fminf(fminf(fabsf(v[a]), fabsf(v[a + 2])), rest[k]);
+                m[a + 2] = fminf(fminf(fabsf(v[a]), fabsf(v[a + 1])), rest[k]);
+            } else if (a + 1 < DEG) {
+                m[a] = fminf(fabsf(v[a + 1]), rest[k]);
+                m[a + 1] = fminf(fabsf(v[a]), rest[k]);
+            } else m[a] = rest[k];
+        }
+    }
+    template <int J, int Q>
+    static __device__ __forceinline__ void phase2o(float* softn, unsigned* hbw, bool lane0, bool active,
+                                                   const float (&v)[K::RP[J + 1] - K::RP[J]], const unsigned (&msg)[K::RP[J + 1] - K::RP[J]])
+    {
+        constexpr int DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q + 1 < DEG) {
+            float n0, n1;
+            add_f32x2(n0, n1, v[Q], v[Q + 1], __uint_as_float(msg[Q]), __uint_as_float(msg[Q + 1]));    // :5199-5204
+            put_posterior<J, Q>(softn, hbw, lane0, active, n0);
+            put_posterior<J, Q + 1>(softn, hbw, lane0, active, n1);
+            phase2o<J, Q + 2>(softn, hbw, lane0, active, v, msg);
+        } else if constexpr (Q < DEG) {
+            put_posterior<J, Q>(softn, hbw, lane0, active, v[Q] + __uint_as_float(msg[Q]));
+        }
+    }
+
     template <int J>
     static __device__ __forceinline__ void layer(float* softn, unsigned* hbw, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active,
                                                  const float (&pre)[NDEG<J>], float (&nxt)[NDEG<J + 1>])
@@ -296,6 +354,31 @@ struct LmsTmem {
             sub_f32x2(v[q], v[q + 1], sv[q], sv[q + 1], __uint_as_float(msg[q]), __uint_as_float(msg[q + 1]));
         if constexpr (DEG & 1) v[DEG - 1] = sv[DEG - 1] - __uint_as_float(msg[DEG - 1]);
         loads_done(mbar, lane0);
+#if LMS_TMEM_OTHERS
+        // the message of edge q is f(min over the OTHER edges of |v2c|), f(x) = min(max(x - 0.4, 0), 32767) (:5166-5168,
+        // :5131-5137): three-input minima over groups of three edges (FMNMX3, |.| is an operand modifier), one per edge,
+        // instead of tracking the two smallest and selecting per edge.  The ceiling is folded into the per-group
+        // "rest" term as CAP = 32767.3984375, the smallest float whose x - 0.4f rounds to 32767 or more (it rounds to
+        // exactly 32767.0, and every smaller float to less).  Offset, floor and the row's sign product s = +-1 are two
+        // FFMAs: th = m * (s/2) - 0.4f * (s/2) = s * (m - 0.4f) / 2 with the same single rounding as m - 0.4f (scaling
+        // by 1/2 is exact), r = |th| * s + th = s * max(m - 0.4f, 0) exactly; the edge's own sign is one LOP3.  Same
+        // posteriors and decisions bit for bit as the two-smallest form (tests/test_gpu_tmem.py); a zero message may
+        // carry the other sign, which no later operation can see (x - (+-0) = x, and a posterior is never -0).
+        // 4.1 instead of 6.9 instructions per edge on the half-rate ALU pipe, 11.8 instead of 12.8 in total.
+        float m[DEG];
+        const unsigned sacc = sign_xor<DEG, 0, DEG>(v) & 0x80000000u;
+        const float rone = __uint_as_float(sacc | 0x3f800000u), rhalf = __fmul_rn(rone, 0.5f);
+        const float nhalf = __fmul_rn(rhalf, -0.4f);                                             // exact: -(s/2) * 0.4f
+        min_of_others<DEG>(v, m, 32767.3984375f);
+        if constexpr (B % 2 == 0) wait_loads(mbar, J & 1);
+        else { wait_loads(mbar, ph); ph ^= 1u; }
+#pragma unroll
+        for (int q = 0; q < DEG; q++) {
+            const float th = __fmaf_rn(m[q], rhalf, nhalf);
+            msg[q] = __float_as_uint(__fmaf_rn(fabsf(th), rone, th)) ^ (__float_as_uint(v[q]) & 0x80000000u);
+        }
+        phase2o<J, 0>(softn, hbw, lane0, active, v, msg);
+#else
         const typename S::RowAcc a = two_smallest<DEG, 0, DEG>(v);
         const unsigned sacc = sign_xor<DEG, 0, DEG>(v);
         const float n1 = fminf(fmaxf(a.c1 - 0.4f, 0.0f), 32767.0f);                              // :5166-5168, :5131-5137
@@ -305,6 +388,7 @@ struct LmsTmem {
         if constexpr (B % 2 == 0) wait_loads(mbar, J & 1);
         else { wait_loads(mbar, ph); ph ^= 1u; }
         phase2<J, 0>(softn, hbw, lane0, active, v, a.c1, m1x, m2x, msg);
+#endif
         tmem_st_n<DEG>(trow + E0, msg);                                                          // :5179
     }
 

@@ -135,22 +135,27 @@ struct MsTmem {
                 if constexpr (IS_INT) v[q] = __fsub_rn(rs[q], __uint_as_float(msg[q]));          // :5646, the message is already scaled (:5640)
                 else v[q] = __fsub_rn(rs[q], __fmul_rn(__uint_as_float(msg[q]), sp.alpha));      // :4714-4722
             }
-            const typename S::RowAcc a = T::template two_smallest<DEG, 0, DEG>(v);               // :4732-4746 / :5656-5666
-            const unsigned rsg = T::template sign_xor<DEG, 0, DEG>(v) & 0x80000000u;
-            float n1, n2;
             if constexpr (IS_INT) {
+                const typename S::RowAcc a = T::template two_smallest<DEG, 0, DEG>(v);           // :5656-5666
+                const unsigned rsg = T::template sign_xor<DEG, 0, DEG>(v) & 0x80000000u;
                 const float mx = (float)sp.max_data, scale = (float)sp.ialpha * 0.0625f;
-                n1 = floorf(__fmul_rn(fminf(a.c1, mx), scale));                                  // :5653, (min * ialpha) >> 4 :5554
-                n2 = floorf(__fmul_rn(fminf(a.c2, mx), scale));
-            } else {
-                n1 = fminf(a.c1, 32767.0f);                                                      // :4730, init :4692-4696
-                n2 = fminf(a.c2, 32767.0f);
-            }
-            const unsigned m1x = __float_as_uint(n1) ^ rsg, m2x = __float_as_uint(n2) ^ rsg;
+                const float n1 = floorf(__fmul_rn(fminf(a.c1, mx), scale));                      // :5653, (min * ialpha) >> 4 :5554
+                const float n2 = floorf(__fmul_rn(fminf(a.c2, mx), scale));
+                const unsigned m1x = __float_as_uint(n1) ^ rsg, m2x = __float_as_uint(n2) ^ rsg;
 #pragma unroll
-            for (int q = 0; q < DEG; q++) {
-                const bool ismin = fabsf(v[q]) == a.c1;
-                msg[q] = (ismin ? m2x : m1x) ^ (__float_as_uint(v[q]) & 0x80000000u);            // c2v sign = sign(v2c) ^ row sign
+                for (int q = 0; q < DEG; q++) {
+                    const bool ismin = fabsf(v[q]) == a.c1;
+                    msg[q] = (ismin ? m2x : m1x) ^ (__float_as_uint(v[q]) & 0x80000000u);        // c2v sign = sign(v2c) ^ row sign
+                }
+            } else {
+                // the message of an edge = min(32767, min over the OTHER edges of |v2c|) with the row's sign product
+                // (a multiplication by +-1) and the edge's own sign: lms_tmem.cuh min_of_others, one FMNMX3 per edge
+                float m[DEG];
+                const float rone = __uint_as_float((T::template sign_xor<DEG, 0, DEG>(v) & 0x80000000u) | 0x3f800000u);
+                T::template min_of_others<DEG>(v, m, 32767.0f);                                  // :4730-4746, init :4692-4696
+#pragma unroll
+                for (int q = 0; q < DEG; q++)
+                    msg[q] = __float_as_uint(__fmul_rn(m[q], rone)) ^ (__float_as_uint(v[q]) & 0x80000000u);
             }
             bad |= synd;
             tmem_st_n<DEG>(trow + E0, msg);                                                      // :4753 / :5675
