@@ -43,9 +43,9 @@ FRAMES_PER_GPU = 1 << 20
 METRIC, UNIT = "decoded_info_gbps_10iter", "Gbit/s"
 TRAFFIC_BYTES_PER_FRAME = (2148866000 + 16032256) / 65536        # ncu capture of the bench kernel (lmst_spec_c2t): 33 034 B per frame
 # SASS instruction mix of one iteration of the bench kernel (tools/sass_mix.py on the built object; profiles/):
-# (ALU-pipe, total) instructions per edge update and lane
-SASS_MIX = {True: (6.94, 12.84, "lms_tmem (profiles/r01_lms_tmem_v7_ncu.txt, tools/sass_mix.py)"),
-            False: (13.9, 25.6, "lms_spec (profiles/r01_lms_spec_v1_ncu.txt)")}
+# (ALU-pipe, total, shared-memory) instructions per edge update and lane
+SASS_MIX = {True: (4.10, 12.02, 3.20, "lms_tmem, min-of-others form (tools/sass_mix.py on lmst_spec_c2t; profiles/r01_lms_tmem_v8_ncu.txt)"),
+            False: (13.9, 25.6, None, "lms_spec (profiles/r01_lms_spec_v1_ncu.txt)")}
 
 
 def load_binding():
@@ -293,7 +293,10 @@ def run_ours(args):
         sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
         edge_updates = frames * dec.E * Z * MAXITER / (kernel_ms * 1e-3)
         issue_peak = 148 * 4 * 32 * sm_hz * 1e6                      # thread-instructions / s
-        alu_ops, all_ops, mix_src = SASS_MIX[bool(info.get("tmem"))]
+        alu_ops, all_ops, lsu_ops, mix_src = SASS_MIX[bool(info.get("tmem"))]
+        fr = {"alu_pipe": edge_updates * alu_ops / (148 * 64 * sm_hz * 1e6), "issue_slots": edge_updates * all_ops / issue_peak}
+        if lsu_ops:
+            fr["shared_memory_wavefronts"] = edge_updates * lsu_ops / (148 * 32 * sm_hz * 1e6)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world, frames),
@@ -313,16 +316,17 @@ def run_ours(args):
                                            "call": "ldpcb200_simulate, reference semantics (max 10 iterations, syndrome early exit)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": TRAFFIC_BYTES_PER_FRAME * frames, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame,
-                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_tmem_v7_ncu.txt (ncu --set full, "
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_tmem_v8_ncu.txt (ncu --set full, "
                                                "65536 frames) scaled to this launch"},
-                # the binding roofline: min-sum is compare / select / logic work that issues on the
-                # ALU pipe (64 lanes / clk / SM); ALU-pipe and total SASS instructions per edge update of the kernel
-                # that ran (SASS_MIX above)
-                "issue": {"bound": "alu_pipe", "edge_updates_per_s": edge_updates, "alu_ops_per_edge_update": alu_ops,
-                          "instr_per_edge_update": all_ops, "source": mix_src,
-                          "alu_lane_peak_per_s": 148 * 64 * sm_hz * 1e6,
-                          "frac": edge_updates * alu_ops / (148 * 64 * sm_hz * 1e6),
-                          "thread_instr_peak_per_s": issue_peak, "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
+                # the binding rooflines: min-sum is compare / logic / shared-memory work.  Per SM and clock:
+                # 4 x 32 thread-instructions issue, the ALU pipe takes 64 lanes, shared memory one 32-lane wavefront.
+                # Instructions per edge update of the kernel that ran (SASS_MIX above) x measured edge updates / s against
+                # each of the three; `frac` is the largest.
+                "issue": {"bound": max(fr, key=fr.get), "frac": max(fr.values()), "fracs": fr,
+                          "edge_updates_per_s": edge_updates, "alu_ops_per_edge_update": alu_ops,
+                          "instr_per_edge_update": all_ops, "shared_memory_ops_per_edge_update": lsu_ops, "source": mix_src,
+                          "alu_lane_peak_per_s": 148 * 64 * sm_hz * 1e6, "thread_instr_peak_per_s": issue_peak,
+                          "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(dec, llr, hard, iters, K)
         emit(line)

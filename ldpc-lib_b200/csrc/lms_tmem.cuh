@@ -358,8 +358,8 @@ struct LmsTmem {
         // the message of edge q is f(min over the OTHER edges of |v2c|), f(x) = min(max(x - 0.4, 0), 32767) (:5166-5168,
         // :5131-5137): three-input minima over groups of three edges (FMNMX3, |.| is an operand modifier), one per edge,
         // instead of tracking the two smallest and selecting per edge.  The ceiling is folded into the per-group
-        // "rest" term as CAP = 32767.3984375, the smallest float whose x - 0.4f rounds to 32767 or more (it rounds to
-        // exactly 32767.0, and every smaller float to less).  Offset, floor and the row's sign product s = +-1 are two
+        // "rest" term as CAP = 32767 + 205/512, the smallest float whose x - 0.4f rounds to 32767 or more (it rounds to
+        // exactly 32767.0, and every smaller float to less; tests/test_message_forms.py).  Offset, floor and the row's sign product s = +-1 are two
         // FFMAs: th = m * (s/2) - 0.4f * (s/2) = s * (m - 0.4f) / 2 with the same single rounding as m - 0.4f (scaling
         // by 1/2 is exact), r = |th| * s + th = s * max(m - 0.4f, 0) exactly; the edge's own sign is one LOP3.  Same
         // posteriors and decisions bit for bit as the two-smallest form (tests/test_gpu_tmem.py); a zero message may
@@ -369,7 +369,7 @@ struct LmsTmem {
         const unsigned sacc = sign_xor<DEG, 0, DEG>(v) & 0x80000000u;
         const float rone = __uint_as_float(sacc | 0x3f800000u), rhalf = __fmul_rn(rone, 0.5f);
         const float nhalf = __fmul_rn(rhalf, -0.4f);                                             // exact: -(s/2) * 0.4f
-        min_of_others<DEG>(v, m, 32767.3984375f);
+        min_of_others<DEG>(v, m, 32767.400390625f);
         if constexpr (B % 2 == 0) wait_loads(mbar, J & 1);
         else { wait_loads(mbar, ph); ph ^= 1u; }
 #pragma unroll

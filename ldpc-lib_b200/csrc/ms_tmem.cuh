@@ -135,23 +135,23 @@ struct MsTmem {
                 if constexpr (IS_INT) v[q] = __fsub_rn(rs[q], __uint_as_float(msg[q]));          // :5646, the message is already scaled (:5640)
                 else v[q] = __fsub_rn(rs[q], __fmul_rn(__uint_as_float(msg[q]), sp.alpha));      // :4714-4722
             }
+            // the message of an edge = g(min over the OTHER edges of |v2c|) with the row's sign product and the edge's
+            // own sign (lms_tmem.cuh min_of_others: one FMNMX3 per edge instead of two-smallest tracking + a select)
+            float m[DEG];
+            const float rone = __uint_as_float((T::template sign_xor<DEG, 0, DEG>(v) & 0x80000000u) | 0x3f800000u);
             if constexpr (IS_INT) {
-                const typename S::RowAcc a = T::template two_smallest<DEG, 0, DEG>(v);           // :5656-5666
-                const unsigned rsg = T::template sign_xor<DEG, 0, DEG>(v) & 0x80000000u;
-                const float mx = (float)sp.max_data, scale = (float)sp.ialpha * 0.0625f;
-                const float n1 = floorf(__fmul_rn(fminf(a.c1, mx), scale));                      // :5653, (min * ialpha) >> 4 :5554
-                const float n2 = floorf(__fmul_rn(fminf(a.c2, mx), scale));
-                const unsigned m1x = __float_as_uint(n1) ^ rsg, m2x = __float_as_uint(n2) ^ rsg;
+                // g(c) = (min(c, max_data) * ialpha) >> 4 (:5653, :5554, :5656-5666) on integers carried as floats:
+                // t = fma(c, ialpha / 16, 1.5 * 2^23) rounded DOWN is 1.5 * 2^23 + floor(c * ialpha / 16) exactly (ulp 1 up
+                // there); the second fma takes the constant off again and applies the row sign: +-floor(x), exact.
+                const float MAGIC = 12582912.0f;
+                const float scale = (float)sp.ialpha * 0.0625f, nmag = __fmul_rn(rone, -MAGIC);
+                T::template min_of_others<DEG>(v, m, (float)sp.max_data);
 #pragma unroll
                 for (int q = 0; q < DEG; q++) {
-                    const bool ismin = fabsf(v[q]) == a.c1;
-                    msg[q] = (ismin ? m2x : m1x) ^ (__float_as_uint(v[q]) & 0x80000000u);        // c2v sign = sign(v2c) ^ row sign
+                    const float t = __fmaf_rd(m[q], scale, MAGIC);
+                    msg[q] = __float_as_uint(__fmaf_rn(t, rone, nmag)) ^ (__float_as_uint(v[q]) & 0x80000000u);
                 }
             } else {
-                // the message of an edge = min(32767, min over the OTHER edges of |v2c|) with the row's sign product
-                // (a multiplication by +-1) and the edge's own sign: lms_tmem.cuh min_of_others, one FMNMX3 per edge
-                float m[DEG];
-                const float rone = __uint_as_float((T::template sign_xor<DEG, 0, DEG>(v) & 0x80000000u) | 0x3f800000u);
                 T::template min_of_others<DEG>(v, m, 32767.0f);                                  // :4730-4746, init :4692-4696
 #pragma unroll
                 for (int q = 0; q < DEG; q++)

@@ -1,0 +1,79 @@
+"""The algebra behind the message computation of the tensor-memory min-sum kernels (csrc/lms_tmem.cuh min_of_others,
+csrc/ms_tmem.cuh pass C), checked in numpy fp32 on the CPU: the kernels compute a message as g(min over the OTHER edges)
+with the ceiling folded into a constant, offset / floor / sign as two fused multiply-adds, and IMS_DEC's shift as a
+round-down fma -- each must equal the reference's two-smallest form (decoders.cpp:5163-5198, :5653) value for value."""
+import numpy as np
+
+f32 = np.float32
+CAP = f32(32767.0) + f32(205.0) / f32(512.0)          # lms_tmem.cuh: 32767.400390625f
+
+
+def lms_reference_form(c):
+    """min(max(c - 0.4, 0), 32767) in fp32 (offset, floor, ceiling of lmin_sum_decod_qc_lm)."""
+    return np.minimum(np.maximum((c - f32(0.4)).astype(f32), f32(0)), f32(32767))
+
+
+def fma32(a, b, c):
+    """fp32 fused multiply-add through float64: the product of two floats is exact in double, and so is the sum
+    for the magnitudes used here (< 2^17 with steps >= 2^-30); one rounding to fp32."""
+    return (a.astype(np.float64) * np.float64(b) + np.float64(c)).astype(f32)
+
+
+def lms_kernel_form(c, s):
+    """s * max(min(c, CAP) - 0.4, 0) as the kernel computes it: two FFMAs, s = +-1."""
+    m = np.minimum(c, CAP)
+    rhalf = f32(s) * f32(0.5)
+    nhalf = rhalf * f32(-0.4)
+    th = fma32(m, rhalf, nhalf)
+    return fma32(np.abs(th), f32(s), th)
+
+
+def test_folded_ceiling_is_the_smallest_float_that_reaches_32767():
+    assert float(CAP) == 32767.400390625
+    assert (CAP - f32(0.4)).astype(f32) == f32(32767.0)
+    below = np.nextafter(CAP, f32(0))
+    assert (below - f32(0.4)).astype(f32) < f32(32767.0)
+
+
+def test_lms_message_magnitude_forms_agree():
+    rng = np.random.default_rng(5)
+    # every float from 32766 to 32769 (step 2^-9), the region around the offset, and a broad random sample
+    around_cap = np.arange(32766 * 512, 32769 * 512 + 1, dtype=np.int64).astype(np.float64) / 512.0
+    c = np.concatenate([around_cap.astype(f32),
+                        np.linspace(0, 1, 200001).astype(f32),
+                        np.abs(rng.normal(0, 30, 400000)).astype(f32),
+                        np.abs(rng.normal(0, 1e5, 100000)).astype(f32),
+                        np.array([0.0, 0.4, np.nextafter(f32(0.4), f32(1)), np.nextafter(f32(0.4), f32(0)), 1e30, 3.4e38], f32)])
+    want = lms_reference_form(c)
+    for s in (1.0, -1.0):
+        got = lms_kernel_form(c, s)
+        assert np.array_equal(np.abs(got), want)
+        assert np.all((got == 0) | (np.sign(got) == s))
+
+
+def test_min_over_others_equals_two_smallest_selection():
+    rng = np.random.default_rng(6)
+    for deg in (1, 2, 3, 4, 7, 8, 13, 19):
+        v = rng.normal(0, 3, (2000, deg)).astype(f32)
+        v[::7, 0] = v[::7, -1]                                      # ties between the two smallest
+        a = np.abs(v)
+        order = np.sort(a, axis=1)
+        c1 = order[:, 0]
+        c2 = order[:, 1] if deg > 1 else np.full(len(v), np.inf, f32)
+        first = np.argmin(a, axis=1)                                 # the reference's position of the first minimum
+        want = np.where(np.arange(deg)[None, :] == first[:, None], c2[:, None], c1[:, None])
+        got = np.stack([np.min(np.delete(a, q, axis=1), axis=1, initial=np.inf) for q in range(deg)], axis=1)
+        assert np.array_equal(want, got)
+
+
+def test_ims_shift_as_round_down_fma():
+    """(min(c, max_data) * ialpha) >> 4 on integers carried as floats: fma(c, ialpha / 16, 1.5 * 2^23) rounded down."""
+    magic = np.float64(12582912.0)
+    for ialpha in (1, 7, 12, 13, 16, 31):
+        c = np.arange(0, 4096, dtype=np.int64)
+        want = (c * ialpha) >> 4
+        exact = c.astype(np.float64) * (ialpha * 0.0625) + magic     # exact in double
+        t = np.floor(exact)                                          # fp32 grid up there is the integers: round-down = floor
+        assert np.all(t < 2 ** 24)
+        got = (t.astype(f32) - f32(magic)).astype(np.int64)
+        assert np.array_equal(got, want)
