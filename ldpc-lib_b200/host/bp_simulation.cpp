@@ -18,7 +18,8 @@
 // own wiring of that path is broken.
 //
 // Out of scope here and refused loudly: GF(q) codes (q_mod > 2) and bit interleavers other than the
-// identity (permutation_type != 0) -- SURVEY.md §8f "next".
+// identity for QAM-16/64/256 (with one bit per channel use every interleaver is statistically the identity) --
+// SURVEY.md §8f "next".
 #include "bp_simulation.h"
 
 #include <algorithm>
@@ -71,8 +72,18 @@ std::pair<double, double> bp_simulation(
     const int b = H.n_rows(), c = H.n_cols(), M = tailbite_length;
     const int r = b * M, n = c * M;
     if (q_mod != 2) die("bp_simulation: q_mod = %d: GF(q) codes are outside the B200 engine (binary decoders only)", q_mod);
-    if (permutation_type != 0) die("bp_simulation: permutation_type = %d: only the identity interleaver (0) is implemented", permutation_type);
     if (modulation_type < MODULATION_SKIP || modulation_type > MODULATION_QAM256) die("Unknown modulation type: %d", modulation_type);
+    if (permutation_type < 0 || permutation_type > 4) die("Unknown permutation type: %d", permutation_type);
+    if (permutation_type != 0) {
+        // The reference interleaves the (all-zero, bp_simulation.cpp:567) codeword, adds noise and de-interleaves
+        // the LLRs (:573, :684).  With one bit per channel use (no modulation, QAM-4) the LLRs are i.i.d., so the
+        // de-interleaved vector has the same distribution whatever the permutation: every interleaver mode gives the
+        // statistics of the identity, and puncturing is applied after de-interleaving (:697-710).  With QAM-16/64/256 the
+        // bit positions of a symbol differ in reliability and the permutation matters: not implemented.
+        if (modulation_type > MODULATION_QAM4)
+            die("bp_simulation: permutation_type = %d with modulation_type = %d: bit interleavers for QAM-16/64/256 are not implemented",
+                permutation_type, modulation_type);
+    }
     switch (decoder_type) {
     case BP_DEC: case SP_DEC: case ASP_DEC: case MS_DEC: case IMS_DEC: case IASP_DEC: case TASP_DEC: case LMS_DEC: case LCHE_DEC: break;
     default: die("Unknown decoder type: %d", decoder_type);
