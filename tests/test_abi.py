@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -159,3 +160,28 @@ def test_runtime_generator_emits_the_same_tensor_memory_tables_as_the_build_time
             assert (cur[col[e]] + delta[e]) % Z == sh[e]
             cur[col[e]] = sh[e]
         assert cur == rot
+
+
+def test_bench_kernel_sass_uses_tensor_memory_and_stays_within_its_instruction_budget():
+    """The SASS of the ahead-of-time bench kernel (lmst_spec_c2t): tensor-memory loads / stores (LDTM / STTM =
+    tcgen05.ld / st), three-input minima, packed adds, no local-memory spills, and the per-edge instruction count that
+    DESIGN.md §4.0 and bench.py's `issue` block quote (tools/sass_mix.py)."""
+    import re
+    import shutil
+    import subprocess
+    obj = os.path.join(ROOT, "ldpc-lib_b200", "build", "lms_spec_aot.o")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(obj) or not os.path.exists(cuobjdump):
+        pytest.skip("no build directory / cuobjdump")
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "lmst_spec_c2t", obj], capture_output=True, text=True, check=True).stdout
+    ops = re.findall(r"^\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", sass, re.M)
+    assert len(ops) > 1000
+    for needed in ("LDTM", "STTM", "FMNMX3", "FADD2", "FFMA", "SYNCS"):
+        assert needed in ops, needed
+    first, last = ops.index("LDTM"), len(ops) - 1 - ops[::-1].index("STTM")
+    body = ops[first:last + 1]                                        # the iterations (the frame load's staging array is stack)
+    assert "LDL" not in body and "STL" not in body                    # nothing spilled in the layers
+    mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_mix.py"), "128"], input=sass, capture_output=True, text=True, check=True).stdout
+    per_edge = float(re.search(r"\(([\d.]+) per edge\)", mix).group(1))
+    alu = float(re.search(r"alu\s+\d+\s+([\d.]+) per edge", mix).group(1))
+    assert per_edge <= 12.5 and alu <= 4.5, mix
