@@ -370,13 +370,13 @@ struct LmsTmem {
         const float rone = __uint_as_float(sacc | 0x3f800000u), rhalf = __fmul_rn(rone, 0.5f);
         const float nhalf = __fmul_rn(rhalf, -0.4f);                                             // exact: -(s/2) * 0.4f
         min_of_others<DEG>(v, m, 32767.400390625f);
-        if constexpr (B % 2 == 0) wait_loads(mbar, J & 1);
-        else { wait_loads(mbar, ph); ph ^= 1u; }
 #pragma unroll
         for (int q = 0; q < DEG; q++) {
             const float th = __fmaf_rn(m[q], rhalf, nhalf);
             msg[q] = __float_as_uint(__fmaf_rn(fabsf(th), rone, th)) ^ (__float_as_uint(v[q]) & 0x80000000u);
         }
+        if constexpr (B % 2 == 0) wait_loads(mbar, J & 1);                                       // before the first store
+        else { wait_loads(mbar, ph); ph ^= 1u; }
         phase2o<J, 0>(softn, hbw, lane0, active, v, msg);
 #else
         const typename S::RowAcc a = two_smallest<DEG, 0, DEG>(v);
