@@ -67,7 +67,7 @@ bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_b
 FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm, int smem_per_block, int allow_jit, const DecParams& dp)
 {
     FastPlan p;
-    if (kind == 1 && precision != 32) return p;             // the double MS_DEC stays on the bit-exact table-driven kernel
+    if (kind == 1 && precision != 32) return p;             // the double MS_DEC has its own kernel (tasp_fast.cu ms64_fast_kernel)
     const char* no_spec = getenv("LDPCB200_NO_SPEC");
     if (no_spec && *no_spec == '1') return p;
     const char* no_tmem = getenv("LDPCB200_NO_TMEM");       // 1: keep the check state register-compressed (ms_spec.cuh)
