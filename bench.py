@@ -41,7 +41,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CODE, Z, SNR_DB, MAXITER, DECODER = "ref32x16_b", 256, 2.0, 10, 8      # 8 = LMS_DEC
 FRAMES_PER_GPU = 1 << 20
 METRIC, UNIT = "decoded_info_gbps_10iter", "Gbit/s"
-TRAFFIC_BYTES_PER_FRAME = (2148866000 + 16032256) / 65536        # ncu capture of the bench kernel (lmst_spec_c2t): 33 034 B per frame
+TRAFFIC_BYTES_PER_FRAME = (2148179000 + 14701312) / 65536        # ncu capture of the bench kernel (lmst_spec_c2t, v8): 33 003 B per frame
 # SASS instruction mix of one iteration of the bench kernel (tools/sass_mix.py on the built object; profiles/):
 # (ALU-pipe, total, shared-memory) instructions per edge update and lane
 SASS_MIX = {True: (4.10, 12.02, 3.20, "lms_tmem, min-of-others form (tools/sass_mix.py on lmst_spec_c2t; profiles/r01_lms_tmem_v8_ncu.txt)"),
