@@ -77,9 +77,11 @@ FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm,
         const double ialpha = (double)(int)(dp.alpha * 16), max_data = (double)((1L << (dp.dbits - 1)) - 1);
         if (!(dp.alpha >= 0) || ialpha * max_data >= 16777216.0) tmem = false;
     }
-    int aot = tmem ? find_lms_spec_aot(g, kind + 3) : -1;   // 4 / 5: messages in tensor memory (ms_tmem.cuh)
+    const char* no_aot = getenv("LDPCB200_NO_AOT");         // 1 (development): compile at run time even when an ahead-of-time instance exists
+    const bool use_aot = !(no_aot && *no_aot == '1' && allow_jit);
+    int aot = (tmem && use_aot) ? find_lms_spec_aot(g, kind + 3) : -1;   // 4 / 5: messages in tensor memory (ms_tmem.cuh)
     if (aot >= 0) p.tmem = 1;
-    else aot = find_lms_spec_aot(g, kind);
+    else if (use_aot) aot = find_lms_spec_aot(g, kind);
     if (aot >= 0) {
         int minb = 1;
         lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);

@@ -353,8 +353,9 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
     const char* no_spec = getenv("LDPCB200_NO_SPEC");
     const char* no_tmem = getenv("LDPCB200_NO_TMEM");       // 1: keep the c2v messages register-compressed (lms_spec.cuh)
     const bool tmem = !(no_tmem && *no_tmem == '1');
+    const char* no_aot = getenv("LDPCB200_NO_AOT");         // 1 (development): compile at run time even when an ahead-of-time instance exists
     int aot = -1;
-    if (!(no_spec && *no_spec == '1')) {
+    if (!(no_spec && *no_spec == '1') && !(no_aot && *no_aot == '1' && allow_jit)) {
         if (tmem) aot = find_lms_spec_aot(g, 3);            // messages in tensor memory (lms_tmem.cuh)
         if (aot >= 0) p.tmem = 1;
         else aot = find_lms_spec_aot(g, 0);

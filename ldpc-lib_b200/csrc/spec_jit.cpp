@@ -166,8 +166,14 @@ bool lms_spec_compile(const std::string& gen, int major, int minor, std::vector<
     char arch[64];
     // B200 is compute capability 10.0 -> sm_100a (architecture-specific features allowed)
     snprintf(arch, sizeof arch, "--gpu-architecture=sm_%d%d%s", major, minor, major >= 9 ? "a" : "");
-    const char* opts[] = { arch, "--std=c++17", "-lineinfo", "-fmad=false" };
-    int rc = n.CompileProgram(prog, 4, opts);
+    std::vector<std::string> extra;                               // LDPCB200_JIT_DEFINES="-DA=1 -DB=0" (development: A/B of kernel variants)
+    if (const char* d = getenv("LDPCB200_JIT_DEFINES")) {
+        std::istringstream is(d);
+        for (std::string tok; is >> tok;) extra.push_back(tok);
+    }
+    std::vector<const char*> opts = { arch, "--std=c++17", "-lineinfo", "-fmad=false" };
+    for (const std::string& e : extra) opts.push_back(e.c_str());
+    int rc = n.CompileProgram(prog, (int)opts.size(), opts.data());
     if (rc != 0) {
         size_t ls = 0;
         n.GetProgramLogSize(prog, &ls);
@@ -193,7 +199,8 @@ const void* lms_spec_jit(const QcHost& g, int zp, int minb, int variant, int kin
     cudaDeviceProp prop;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { why = "no device"; return nullptr; }
     const std::string gen = lms_spec_generate(g, zp, minb, variant, kind);
-    const std::string key = std::to_string(dev) + "\n" + gen;
+    const char* defs = getenv("LDPCB200_JIT_DEFINES");
+    const std::string key = std::to_string(dev) + "\n" + (defs ? defs : "") + "\n" + gen;
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) return (const void*)it->second.kernel;

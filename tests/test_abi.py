@@ -185,3 +185,23 @@ def test_bench_kernel_sass_uses_tensor_memory_and_stays_within_its_instruction_b
     per_edge = float(re.search(r"\(([\d.]+) per edge\)", mix).group(1))
     alu = float(re.search(r"alu\s+\d+\s+([\d.]+) per edge", mix).group(1))
     assert per_edge <= 12.5 and alu <= 4.5, mix
+
+
+def test_jit_defines_reach_the_run_time_compilation():
+    """LDPCB200_JIT_DEFINES (development switch): macro definitions handed to NVRTC change the kernel
+    that is built -- here the two-smallest form of lms_tmem's message computation instead of the minima over the other
+    edges; both compile for sm_100a without a device."""
+    code = ("import sys, ctypes as C, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); "
+            "from codes import load_code; import pyldpcb200 as L; hd = np.ascontiguousarray(load_code('ref32x16_b')[0], np.int16); "
+            "n = C.c_int(0); rc = L.lib().ldpcb200_jit_check(hd.ctypes.data_as(C.POINTER(C.c_int16)), 16, 32, 256, 10, 0, C.byref(n)); "
+            "print(rc, n.value)") % (os.path.join(ROOT, "tests"), os.path.join(ROOT, "ldpc-lib_b200"))
+    sizes = []
+    for defs in ("", "-DLMS_TMEM_OTHERS=0"):
+        env = dict(os.environ, LDPCB200_JIT_DEFINES=defs)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        rc, n = (int(x) for x in r.stdout.split())
+        if rc != 0:
+            pytest.skip("NVRTC not available")
+        sizes.append(n)
+    assert sizes[0] > 0 and sizes[1] > 0 and sizes[0] != sizes[1]
