@@ -77,3 +77,47 @@ def test_ims_shift_as_round_down_fma():
         assert np.all(t < 2 ** 24)
         got = (t.astype(f32) - f32(magic)).astype(np.int64)
         assert np.array_equal(got, want)
+
+
+def grouped_min_of_others(a, cap):
+    """The grouping csrc/lms_tmem.cuh min_of_others uses (groups of three, per-group rest term with the ceiling folded
+    in, prefix / suffix minima from four groups on), restated on numpy columns."""
+    deg = a.shape[1]
+    G = (deg + 2) // 3
+    g = [np.min(a[:, 3 * k:min(3 * k + 3, deg)], axis=1) for k in range(G)]
+    capv = np.full(len(a), cap, f32)
+    if G == 1:
+        rest = [capv]
+    elif G == 2:
+        rest = [np.minimum(g[1], capv), np.minimum(g[0], capv)]
+    elif G == 3:
+        rest = [np.minimum(np.minimum(g[1], g[2]), capv), np.minimum(np.minimum(g[0], g[2]), capv), np.minimum(np.minimum(g[0], g[1]), capv)]
+    else:
+        pre, suf = [capv], [None] * G
+        for k in range(1, G):
+            pre.append(np.minimum(pre[k - 1], g[k - 1]))
+        suf[G - 2] = g[G - 1]
+        for k in range(G - 3, -1, -1):
+            suf[k] = np.minimum(suf[k + 1], g[k + 1])
+        rest = [np.minimum(pre[k], suf[k]) for k in range(G - 1)] + [pre[G - 1]]
+    m = np.empty_like(a)
+    for k in range(G):
+        lo, hi = 3 * k, min(3 * k + 3, deg)
+        for q in range(lo, hi):
+            mates = [p for p in range(lo, hi) if p != q]
+            v = rest[k]
+            for p in mates:
+                v = np.minimum(v, a[:, p])
+            m[:, q] = v
+    return m
+
+
+def test_grouped_minima_cover_every_other_edge_exactly_once():
+    rng = np.random.default_rng(8)
+    for deg in range(1, 25):
+        a = np.abs(rng.normal(0, 3, (500, deg))).astype(f32)
+        a[::5, deg // 2] = a[::5, 0]                                 # ties
+        a[::11] *= f32(2e4)                                          # rows beyond the ceiling
+        for cap in (f32(32767.0), CAP, f32(127.0)):
+            want = np.stack([np.minimum(np.min(np.delete(a, q, axis=1), axis=1, initial=np.inf), cap) for q in range(deg)], axis=1).astype(f32)
+            assert np.array_equal(grouped_min_of_others(a, cap), want), (deg, cap)
