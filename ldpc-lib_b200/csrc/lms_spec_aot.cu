@@ -20,10 +20,12 @@ size_t ms_spec_smem_bytes(int c, int Z);
 size_t lms_tmem_smem_bytes(int b, int c, int Z, int maxdeg)
 {
     const int zp = (Z + 31) / 32 * 32, hw = zp / 32, nb = (Z + 31) / 32, nwarps = zp / 32;
-    const size_t soft = 2 * (size_t)c * Z, hb = (size_t)(c * hw > 3 ? c * hw : 3) + 1;
+    // Z a multiple of 32: two buffers of padded single-copy columns (LmsTmem::PP), else one buffer of doubled columns
+    const bool pp = Z % 32 == 0;
+    const size_t soft = pp ? 2 * (size_t)c * (Z + 32) : 2 * (size_t)c * Z, hb = (size_t)(c * hw > 3 ? c * hw : 3) + 1;
     const size_t plan = (size_t)((b * nb + 8 * nwarps - 1) / (8 * nwarps)) * ((maxdeg + 3) / 4) * zp;
     const size_t mbar = (soft + hb + plan + zp + 1) & ~(size_t)1;     // + the quick-look word per thread
-    return sizeof(float) * (mbar + 2 + 4);
+    return sizeof(float) * (mbar + 2 + 4 + (pp ? c : 0));
 }
 
 // shared memory of MsTmem<K, IS_INT> (ms_tmem.cuh, SMEM_WORDS)

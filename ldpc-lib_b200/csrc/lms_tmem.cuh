@@ -32,6 +32,15 @@
 #ifndef LMS_TMEM_OTHERS
 #define LMS_TMEM_OTHERS 1
 #endif
+#ifndef LMS_TMEM_PP
+#define LMS_TMEM_PP 1           // Z a multiple of 32: padded single-copy columns, two buffers used alternately (see PP below)
+#endif
+#ifndef LMS_TMEM_FFMA2
+#define LMS_TMEM_FFMA2 0        // PP: the offset / scale FFMA of two edges as one fma.rn.f32x2
+#endif
+#ifndef LMS_TMEM_PP_BRANCH
+#define LMS_TMEM_PP_BRANCH 1    // PP: warp 0's repeat stores behind a branch (0: predicated stores in every warp)
+#endif
 
 namespace ldpcb200 {
 
@@ -145,6 +154,16 @@ static __device__ __forceinline__ void sub_f32x2(float& d0, float& d1, float a0,
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 
+static __device__ __forceinline__ void fma_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1)
+{
+    unsigned long long a, b, c, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 template <class K>
 struct LmsTmem {
     using S = LmsSpec<K>;
@@ -153,8 +172,20 @@ struct LmsTmem {
     static constexpr int NB = (Z + 31) / 32;
     static constexpr int NWORDS = (N + 31) / 32;
     static constexpr bool ALL_ACTIVE = (Z == ZP);
-    static constexpr int CS = 2 * Z;
-    static constexpr int SOFT_WORDS = C * CS;
+    // ---- PP layout (Z a multiple of 32).  A block column is Z + 32 words: position p < Z, and positions Z .. Z+31
+    // repeat 0 .. 31.  Lane n = 32w + l reads position (n + DELTA) mod Z, DELTA = 32a + b, as word
+    // 32 * ((w + a) mod NWARPS) + (l + b) <= Z + 30: the warp part is a warp-uniform base (one per value of a, held in
+    // uniform registers), l + b needs no wrap because of the 32 repeated words -- one plain load, as with the doubled
+    // column, but the writer stores ONE word per lane (warp 0 also stores the repeat): 2.125 shared-memory wavefronts
+    // per edge instead of 3.  Every column has two such buffers; a block row reads the column's current buffer and
+    // writes the other one, so no lane can overwrite a word that another warp of the same block row has yet to read
+    // -- the write-after-read hazard that the doubled layout closes with the split mbarrier does not exist.  Which
+    // buffer is current depends on how often the column has been written: (iteration * column weight + edges of the
+    // column above this one) mod 2, a compile-time constant once two consecutive iterations are unrolled (PAR).
+    static constexpr bool PP = LMS_TMEM_PP && (Z % 32 == 0);
+    static constexpr int CS = PP ? Z + 32 : 2 * Z;
+    static constexpr int BUF = C * CS;                        // PP: word offset of the second buffer
+    static constexpr int SOFT_WORDS = PP ? 2 * C * CS : C * CS;
     static constexpr int TCOLS = K::TCOLS;                    // power of two >= 32, >= E * ceil(warps / 4)
     static constexpr int NWARPS = ZP / 32;
     // shared memory (words): posteriors | packed decisions hb (+ one zero word) | syndrome plan | mbarrier (8-byte aligned) | misc
@@ -164,7 +195,8 @@ struct LmsTmem {
     static constexpr int PLAN1_OFF = PLAN_OFF + PLAN_WORDS;      // quick syndrome look (syndrome_quick): one word per thread
     static constexpr int MBAR_OFF = (PLAN1_OFF + ZP + 1) & ~1;
     static constexpr int MISC_OFF = MBAR_OFF + 2;
-    static constexpr int SMEM_WORDS = MISC_OFF + 4;
+    static constexpr int CW_OFF = MISC_OFF + 4;                  // PP: column weights (which buffer holds the result)
+    static constexpr int SMEM_WORDS = CW_OFF + (PP ? C : 0);
 
     // Edge Q of block row J reads a column that block row J - 1 does not write: its value is final once the barrier
     // before block row J - 1 has passed, so the load can be issued one block row early (and its latency hidden behind
@@ -404,6 +436,228 @@ struct LmsTmem {
         }
     }
 
+    // ---- PP block rows.  Compile-time bookkeeping of the two buffers of a column
+    static __host__ __device__ constexpr int touch_index(int e) { int t = 0; for (int i = 0; i < e; i++) t += K::COL[i] == K::COL[e] ? 1 : 0; return t; }
+    static __host__ __device__ constexpr int col_weight(int col) { int t = 0; for (int i = 0; i < E; i++) t += K::COL[i] == col ? 1 : 0; return t; }
+    // the buffer edge e reads in an iteration of parity PAR (it writes the other one)
+    template <int PAR> static __host__ __device__ constexpr int rbuf(int e) { return (PAR * col_weight(K::COL[e]) + touch_index(e)) & 1; }
+
+    // loads of block row J: the edges whose column the previous block row does not write (WANT_EARLY, issued before the
+    // barrier that ends the previous block row) or the others (after it).  softl = buffer 0 + lane, uoff[a] = 32 * ((warp + a) mod NWARPS)
+    template <int J, int PAR, bool WANT_EARLY, int Q = 0>
+    static __device__ __forceinline__ void pp_load(const float* softl, const unsigned (&uoff)[NWARPS], float (&sv)[NDEG<J>])
+    {
+        if constexpr (J < B) {
+            if constexpr (Q < NDEG<J>) {
+                constexpr int e = K::RP[J < B ? J : 0] + Q;
+                if constexpr (K::EARLY[e] == WANT_EARLY) {
+                    constexpr int a = K::DELTA[e] / 32, b = K::DELTA[e] % 32;
+                    constexpr int off = (rbuf<PAR>(e) * C + K::COL[e]) * CS + b;
+                    sv[Q] = softl[uoff[a] + off];
+                }
+                pp_load<J, PAR, WANT_EARLY, Q + 1>(softl, uoff, sv);
+            }
+        }
+    }
+    template <int J, int PAR, int Q = 0>
+    static __device__ __forceinline__ void pp_put(float* softn, unsigned* hbw, bool lane0, const float (&nv)[NDEG<J>])
+    {
+        if constexpr (Q < NDEG<J>) {
+            constexpr int e = K::RP[J] + Q;
+            constexpr int off = ((rbuf<PAR>(e) ^ 1) * C + K::COL[e]) * CS;
+            softn[off] = nv[Q];                                                                  // one word per lane
+            if constexpr (K::LAST[e]) {                                                          // see put_posterior
+                const unsigned w = __ballot_sync(0xffffffffu, nv[Q] < 0.0f);
+                if (lane0) hbw[K::COL[e] * HW] = w;
+            }
+            pp_put<J, PAR, Q + 1>(softn, hbw, lane0, nv);
+        }
+    }
+    template <int J, int PAR, int Q = 0>
+    static __device__ __forceinline__ void pp_repeat_plain(float* softn, const float (&nv)[NDEG<J>])
+    {
+        if constexpr (Q < NDEG<J>) {
+            constexpr int e = K::RP[J] + Q;
+            constexpr int off = ((rbuf<PAR>(e) ^ 1) * C + K::COL[e]) * CS + Z;
+            softn[off] = nv[Q];
+            pp_repeat_plain<J, PAR, Q + 1>(softn, nv);
+        }
+    }
+    // warp 0 repeats its words at positions Z .. Z+31.  The stores sit behind a real branch (inline PTX: the compiler turns
+    // an `if` around a few stores into predicated stores, which would cost the other warps an issue slot each)
+    template <int J, int PAR, int Q>
+    static constexpr int pp_rep_off = 4 * (((rbuf<PAR>(K::RP[J] + (Q < NDEG<J> ? Q : 0)) ^ 1) * C + K::COL[K::RP[J] + (Q < NDEG<J> ? Q : 0)]) * CS + Z);
+    template <int J, int PAR, int Q = 0>
+    static __device__ __forceinline__ void pp_repeat(unsigned softn_s, unsigned notwarp0, const float (&nv)[NDEG<J>])
+    {
+        // a loop that runs once for warp 0 and not at all for the others: the compiler keeps it a branch
+#define REP_HEAD "{\n\t.reg .pred p;\n\t.reg .u32 i;\n\tmov.u32 i, %0;\n\tREP_LOOP:\n\tsetp.ne.u32 p, i, 0;\n\t@p bra.uni REP_DONE;\n\t"
+#define REP_TAIL "add.u32 i, i, 1;\n\tbra.uni REP_LOOP;\n\tREP_DONE:\n\t}"
+        constexpr int DEG = NDEG<J>;
+        if constexpr (Q + 14 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %16;\n\tst.shared.f32 [%1+%3], %17;\n\tst.shared.f32 [%1+%4], %18;\n\tst.shared.f32 [%1+%5], %19;\n\tst.shared.f32 [%1+%6], %20;\n\tst.shared.f32 [%1+%7], %21;\n\tst.shared.f32 [%1+%8], %22;\n\tst.shared.f32 [%1+%9], %23;\n\tst.shared.f32 [%1+%10], %24;\n\tst.shared.f32 [%1+%11], %25;\n\tst.shared.f32 [%1+%12], %26;\n\tst.shared.f32 [%1+%13], %27;\n\tst.shared.f32 [%1+%14], %28;\n\tst.shared.f32 [%1+%15], %29;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>), "n"(pp_rep_off<J, PAR, Q + 7>), "n"(pp_rep_off<J, PAR, Q + 8>), "n"(pp_rep_off<J, PAR, Q + 9>), "n"(pp_rep_off<J, PAR, Q + 10>), "n"(pp_rep_off<J, PAR, Q + 11>), "n"(pp_rep_off<J, PAR, Q + 12>), "n"(pp_rep_off<J, PAR, Q + 13>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]), "f"(nv[Q + 7]), "f"(nv[Q + 8]), "f"(nv[Q + 9]), "f"(nv[Q + 10]), "f"(nv[Q + 11]), "f"(nv[Q + 12]), "f"(nv[Q + 13]) : "memory");
+            pp_repeat<J, PAR, Q + 14>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 13 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %15;\n\tst.shared.f32 [%1+%3], %16;\n\tst.shared.f32 [%1+%4], %17;\n\tst.shared.f32 [%1+%5], %18;\n\tst.shared.f32 [%1+%6], %19;\n\tst.shared.f32 [%1+%7], %20;\n\tst.shared.f32 [%1+%8], %21;\n\tst.shared.f32 [%1+%9], %22;\n\tst.shared.f32 [%1+%10], %23;\n\tst.shared.f32 [%1+%11], %24;\n\tst.shared.f32 [%1+%12], %25;\n\tst.shared.f32 [%1+%13], %26;\n\tst.shared.f32 [%1+%14], %27;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>), "n"(pp_rep_off<J, PAR, Q + 7>), "n"(pp_rep_off<J, PAR, Q + 8>), "n"(pp_rep_off<J, PAR, Q + 9>), "n"(pp_rep_off<J, PAR, Q + 10>), "n"(pp_rep_off<J, PAR, Q + 11>), "n"(pp_rep_off<J, PAR, Q + 12>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]), "f"(nv[Q + 7]), "f"(nv[Q + 8]), "f"(nv[Q + 9]), "f"(nv[Q + 10]), "f"(nv[Q + 11]), "f"(nv[Q + 12]) : "memory");
+            pp_repeat<J, PAR, Q + 13>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 12 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %14;\n\tst.shared.f32 [%1+%3], %15;\n\tst.shared.f32 [%1+%4], %16;\n\tst.shared.f32 [%1+%5], %17;\n\tst.shared.f32 [%1+%6], %18;\n\tst.shared.f32 [%1+%7], %19;\n\tst.shared.f32 [%1+%8], %20;\n\tst.shared.f32 [%1+%9], %21;\n\tst.shared.f32 [%1+%10], %22;\n\tst.shared.f32 [%1+%11], %23;\n\tst.shared.f32 [%1+%12], %24;\n\tst.shared.f32 [%1+%13], %25;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>), "n"(pp_rep_off<J, PAR, Q + 7>), "n"(pp_rep_off<J, PAR, Q + 8>), "n"(pp_rep_off<J, PAR, Q + 9>), "n"(pp_rep_off<J, PAR, Q + 10>), "n"(pp_rep_off<J, PAR, Q + 11>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]), "f"(nv[Q + 7]), "f"(nv[Q + 8]), "f"(nv[Q + 9]), "f"(nv[Q + 10]), "f"(nv[Q + 11]) : "memory");
+            pp_repeat<J, PAR, Q + 12>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 11 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %13;\n\tst.shared.f32 [%1+%3], %14;\n\tst.shared.f32 [%1+%4], %15;\n\tst.shared.f32 [%1+%5], %16;\n\tst.shared.f32 [%1+%6], %17;\n\tst.shared.f32 [%1+%7], %18;\n\tst.shared.f32 [%1+%8], %19;\n\tst.shared.f32 [%1+%9], %20;\n\tst.shared.f32 [%1+%10], %21;\n\tst.shared.f32 [%1+%11], %22;\n\tst.shared.f32 [%1+%12], %23;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>), "n"(pp_rep_off<J, PAR, Q + 7>), "n"(pp_rep_off<J, PAR, Q + 8>), "n"(pp_rep_off<J, PAR, Q + 9>), "n"(pp_rep_off<J, PAR, Q + 10>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]), "f"(nv[Q + 7]), "f"(nv[Q + 8]), "f"(nv[Q + 9]), "f"(nv[Q + 10]) : "memory");
+            pp_repeat<J, PAR, Q + 11>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 10 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %12;\n\tst.shared.f32 [%1+%3], %13;\n\tst.shared.f32 [%1+%4], %14;\n\tst.shared.f32 [%1+%5], %15;\n\tst.shared.f32 [%1+%6], %16;\n\tst.shared.f32 [%1+%7], %17;\n\tst.shared.f32 [%1+%8], %18;\n\tst.shared.f32 [%1+%9], %19;\n\tst.shared.f32 [%1+%10], %20;\n\tst.shared.f32 [%1+%11], %21;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>), "n"(pp_rep_off<J, PAR, Q + 7>), "n"(pp_rep_off<J, PAR, Q + 8>), "n"(pp_rep_off<J, PAR, Q + 9>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]), "f"(nv[Q + 7]), "f"(nv[Q + 8]), "f"(nv[Q + 9]) : "memory");
+            pp_repeat<J, PAR, Q + 10>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 9 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %11;\n\tst.shared.f32 [%1+%3], %12;\n\tst.shared.f32 [%1+%4], %13;\n\tst.shared.f32 [%1+%5], %14;\n\tst.shared.f32 [%1+%6], %15;\n\tst.shared.f32 [%1+%7], %16;\n\tst.shared.f32 [%1+%8], %17;\n\tst.shared.f32 [%1+%9], %18;\n\tst.shared.f32 [%1+%10], %19;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>), "n"(pp_rep_off<J, PAR, Q + 7>), "n"(pp_rep_off<J, PAR, Q + 8>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]), "f"(nv[Q + 7]), "f"(nv[Q + 8]) : "memory");
+            pp_repeat<J, PAR, Q + 9>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 8 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %10;\n\tst.shared.f32 [%1+%3], %11;\n\tst.shared.f32 [%1+%4], %12;\n\tst.shared.f32 [%1+%5], %13;\n\tst.shared.f32 [%1+%6], %14;\n\tst.shared.f32 [%1+%7], %15;\n\tst.shared.f32 [%1+%8], %16;\n\tst.shared.f32 [%1+%9], %17;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>), "n"(pp_rep_off<J, PAR, Q + 7>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]), "f"(nv[Q + 7]) : "memory");
+            pp_repeat<J, PAR, Q + 8>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 7 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %9;\n\tst.shared.f32 [%1+%3], %10;\n\tst.shared.f32 [%1+%4], %11;\n\tst.shared.f32 [%1+%5], %12;\n\tst.shared.f32 [%1+%6], %13;\n\tst.shared.f32 [%1+%7], %14;\n\tst.shared.f32 [%1+%8], %15;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>), "n"(pp_rep_off<J, PAR, Q + 6>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]), "f"(nv[Q + 6]) : "memory");
+            pp_repeat<J, PAR, Q + 7>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 6 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %8;\n\tst.shared.f32 [%1+%3], %9;\n\tst.shared.f32 [%1+%4], %10;\n\tst.shared.f32 [%1+%5], %11;\n\tst.shared.f32 [%1+%6], %12;\n\tst.shared.f32 [%1+%7], %13;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>), "n"(pp_rep_off<J, PAR, Q + 5>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]), "f"(nv[Q + 5]) : "memory");
+            pp_repeat<J, PAR, Q + 6>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 5 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %7;\n\tst.shared.f32 [%1+%3], %8;\n\tst.shared.f32 [%1+%4], %9;\n\tst.shared.f32 [%1+%5], %10;\n\tst.shared.f32 [%1+%6], %11;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>), "n"(pp_rep_off<J, PAR, Q + 4>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]), "f"(nv[Q + 4]) : "memory");
+            pp_repeat<J, PAR, Q + 5>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 4 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %6;\n\tst.shared.f32 [%1+%3], %7;\n\tst.shared.f32 [%1+%4], %8;\n\tst.shared.f32 [%1+%5], %9;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>), "n"(pp_rep_off<J, PAR, Q + 3>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]), "f"(nv[Q + 3]) : "memory");
+            pp_repeat<J, PAR, Q + 4>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 3 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %5;\n\tst.shared.f32 [%1+%3], %6;\n\tst.shared.f32 [%1+%4], %7;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>), "n"(pp_rep_off<J, PAR, Q + 2>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]), "f"(nv[Q + 2]) : "memory");
+            pp_repeat<J, PAR, Q + 3>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 2 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %4;\n\tst.shared.f32 [%1+%3], %5;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>), "n"(pp_rep_off<J, PAR, Q + 1>),
+                            "f"(nv[Q + 0]), "f"(nv[Q + 1]) : "memory");
+            pp_repeat<J, PAR, Q + 2>(softn_s, notwarp0, nv);
+        }
+        else if constexpr (Q + 1 <= DEG) {
+            asm volatile(REP_HEAD "st.shared.f32 [%1+%2], %3;\n\t" REP_TAIL
+                         :: "r"(notwarp0), "r"(softn_s), "n"(pp_rep_off<J, PAR, Q + 0>),
+                            "f"(nv[Q + 0]) : "memory");
+            pp_repeat<J, PAR, Q + 1>(softn_s, notwarp0, nv);
+        }
+#undef REP_HEAD
+#undef REP_TAIL
+    }
+
+    // msg / sv: the row's old messages (tcgen05.ld in flight) and the early posteriors, both issued by the previous block row;
+    // msgn / svn: the same for the next one
+    template <int J, int PAR>
+    static __device__ __forceinline__ void pp_layer(float* softn, const float* softl, const unsigned (&uoff)[NWARPS], unsigned* hbw, unsigned trow,
+                                                    bool lane0, bool warp0, unsigned (&msg)[NDEG<J>], float (&sv)[NDEG<J>],
+                                                    unsigned (&msgn)[NDEG<J + 1>], float (&svn)[NDEG<J + 1>])
+    {
+        constexpr int E0 = K::RP[J], DEG = NDEG<J>;
+        float v[DEG], m[DEG], nv[DEG];
+        pp_load<J, PAR, false>(softl, uoff, sv);
+        tmem_wait_ld<DEG>(msg);
+#pragma unroll
+        for (int q = 0; q + 1 < DEG; q += 2)                                                     // :5152-5158, two edges per FADD2
+            sub_f32x2(v[q], v[q + 1], sv[q], sv[q + 1], __uint_as_float(msg[q]), __uint_as_float(msg[q + 1]));
+        if constexpr (DEG & 1) v[DEG - 1] = sv[DEG - 1] - __uint_as_float(msg[DEG - 1]);
+        const unsigned sacc = sign_xor<DEG, 0, DEG>(v) & 0x80000000u;                            // see layer()
+        const float rone = __uint_as_float(sacc | 0x3f800000u), rhalf = __fmul_rn(rone, 0.5f);
+        const float nhalf = __fmul_rn(rhalf, -0.4f);
+        min_of_others<DEG>(v, m, 32767.400390625f);
+#if LMS_TMEM_FFMA2
+        {
+            float th[DEG];
+#pragma unroll
+            for (int q = 0; q + 1 < DEG; q += 2) fma_f32x2(th[q], th[q + 1], m[q], m[q + 1], rhalf, rhalf, nhalf, nhalf);
+            if constexpr (DEG & 1) th[DEG - 1] = __fmaf_rn(m[DEG - 1], rhalf, nhalf);
+#pragma unroll
+            for (int q = 0; q < DEG; q++)
+                msg[q] = __float_as_uint(__fmaf_rn(fabsf(th[q]), rone, th[q])) ^ (__float_as_uint(v[q]) & 0x80000000u);
+        }
+#else
+#pragma unroll
+        for (int q = 0; q < DEG; q++) {
+            const float th = __fmaf_rn(m[q], rhalf, nhalf);
+            msg[q] = __float_as_uint(__fmaf_rn(fabsf(th), rone, th)) ^ (__float_as_uint(v[q]) & 0x80000000u);
+        }
+#endif
+#pragma unroll
+        for (int q = 0; q + 1 < DEG; q += 2)                                                     // :5199-5204
+            add_f32x2(nv[q], nv[q + 1], v[q], v[q + 1], __uint_as_float(msg[q]), __uint_as_float(msg[q + 1]));
+        if constexpr (DEG & 1) nv[DEG - 1] = v[DEG - 1] + __uint_as_float(msg[DEG - 1]);
+        pp_put<J, PAR>(softn, hbw, lane0, nv);
+#if LMS_TMEM_PP_BRANCH
+        pp_repeat<J, PAR>((unsigned)__cvta_generic_to_shared(softn), warp0 ? 0u : 1u, nv);
+#else
+        if (warp0) pp_repeat_plain<J, PAR>(softn, nv);
+#endif
+        tmem_st_n<DEG>(trow + E0, msg);                                                          // :5179
+        if constexpr (J + 1 < B) {
+            constexpr int E1 = K::RP[J + 1 < B ? J + 1 : 0];
+            tmem_ld_n<NDEG<J + 1>>(trow + E1, msgn);
+            pp_load<J + 1, PAR, true>(softl, uoff, svn);
+        }
+    }
+    template <int J, int PAR>
+    static __device__ __forceinline__ void pp_layers(float* softn, const float* softl, const unsigned (&uoff)[NWARPS], unsigned* hbw, unsigned trow,
+                                                     bool lane0, bool warp0, unsigned (&msg)[NDEG<J>], float (&sv)[NDEG<J>])
+    {
+        if constexpr (J < B) {
+            unsigned msgn[NDEG<J + 1>];
+            float svn[NDEG<J + 1>];
+            pp_layer<J, PAR>(softn, softl, uoff, hbw, trow, lane0, warp0, msg, sv, msgn, svn);
+            __syncthreads();
+            pp_layers<J + 1, PAR>(softn, softl, uoff, hbw, trow, lane0, warp0, msgn, svn);
+        }
+    }
+    template <int PAR>
+    static __device__ __forceinline__ void pp_iteration(float* softn, const float* softl, const unsigned (&uoff)[NWARPS], unsigned* hbw, unsigned trow,
+                                                        bool lane0, bool warp0)
+    {
+        unsigned msg[NDEG<0>];
+        float sv[NDEG<0>];
+        tmem_wait_st();                                                                          // last iteration's messages are in place
+        tmem_ld_n<NDEG<0>>(trow, msg);
+        pp_layers<0, PAR>(softn, softl, uoff, hbw, trow, lane0, warp0, msg, sv);
+    }
+
     // ---- syndrome of the hard decisions on packed bits.  hb[col * HW + w] = signs of positions 32w..32w+31 of
     // column col (the column's rotated order).  During the iterations the words are written by the layers
     // themselves (phase2, K::LAST edges); pack() builds them for the channel values before the first iteration.
@@ -530,9 +784,9 @@ struct LmsTmem {
     }
     static __device__ __forceinline__ void put(float* soft2, int col, int k, float x)
     {
-        const int p = col * CS + pos_of(col, k);
+        const int q = pos_of(col, k), p = col * CS + q;
         soft2[p] = x;
-        soft2[p + Z] = x;
+        if (!PP || q < 32) soft2[p + Z] = x;
     }
 
     static __device__ __forceinline__ void kernel(const FrameIO& io)
@@ -549,6 +803,21 @@ struct LmsTmem {
         unsigned* hbw = hb + (tid >> 5);
         const unsigned mbar = (unsigned)__cvta_generic_to_shared(soft2 + MBAR_OFF);
         unsigned ph = 0;
+        // PP: warp-uniform pieces of the read addresses (the shuffle tells the compiler so)
+        const unsigned wu = __shfl_sync(0xffffffffu, (unsigned)tid >> 5, 0);
+        const bool warp0 = wu == 0;
+        const float* softl = soft2 + (tid & 31);
+        unsigned uoff[NWARPS];
+#pragma unroll
+        for (int a = 0; a < NWARPS; a++) uoff[a] = ((wu + a) % NWARPS) * 32u;
+        int* s_cw = (int*)(soft2 + CW_OFF);
+        if constexpr (PP) {
+            for (int col = tid; col < C; col += ZP) {
+                int wgt = 0;
+                for (int e = 0; e < E; e++) wgt += K::rt_col()[e] == col;
+                s_cw[col] = wgt;
+            }
+        }
         build_plan(plan, tid);
         if (tid == 0) hb[HB_WORDS - 1] = 0u;
         if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"((unsigned)NWARPS) : "memory");
@@ -623,7 +892,7 @@ struct LmsTmem {
                     for (int u = 0; u < 16; u++) {
                         const int col = c0 + u;
                         if (col < C) {
-                            if (act) { softn[col * CS] = x[u]; softn[col * CS + Z] = x[u]; }
+                            if (act) { softn[col * CS] = x[u]; if (!PP || warp0) softn[col * CS + Z] = x[u]; }
                             const unsigned w = __ballot_sync(0xffffffffu, act && x[u] < 0.0f);   // the packed decisions of the
                             if (lane0) hbw[col * HW] = w;                                         // channel values, as pack() builds them
                         }
@@ -639,7 +908,7 @@ struct LmsTmem {
                         if (k >= Z) k -= Z;
                         const float x = (float)__ldcs(y + col * Z + k);
                         softn[col * CS] = x;
-                        softn[col * CS + Z] = x;
+                        if (!PP || warp0) softn[col * CS + Z] = x;
                     }
                 }
             }
@@ -649,28 +918,47 @@ struct LmsTmem {
 
             if (!packed) pack(soft2, hb, tid);
             int parity = syndrome(hb, plan, tid);                                   // :5111-5115
-            int ret = 0, locked = 0, iter;
+            int ret = 0, locked = 0, iter, done = 0;
             if (!parity) { ret = 1; locked = 1; }
+            // One pass of the loop = one iteration (PP: two, so that the buffer every edge uses is a compile-time constant).
+            // With LDPCB200_NO_EARLY_EXIT every iteration and every syndrome check runs (worst-case timing); `ret` keeps
+            // the count at which the reference would have stopped.
+            auto after = [&](void) -> bool {                                            // -> stop
+                done++;
+                const int par = syndrome(hb, plan, tid);                                // :5281-5284
+                if (!locked) { parity = par; if (!par) { ret = iter + 1; locked = 1; } }
+                return !par && !noexit;
+            };
             for (iter = 0; iter < io.maxiter; iter++) {
                 if (!parity && !noexit) break;                                          // :5119
-                tmem_wait_st();                                                         // last iteration's messages are in place
-                { float none[NDEG<0>]; layers<0>(softn, hbw, trow, mbar, ph, lane0, active, none); }
-                if (locked) continue;                                                   // fixed-iteration mode after the first success: the verdict is known
-                parity = syndrome(hb, plan, tid);                                   // :5281-5284
-                if (!parity && !locked) { ret = iter + 1; locked = 1; }
-                if (!parity && !noexit) break;
+                if constexpr (PP) {
+                    pp_iteration<0>(softn, softl, uoff, hbw, trow, lane0, warp0);
+                    if (after()) break;
+                    if (++iter >= io.maxiter) break;
+                    pp_iteration<1>(softn, softl, uoff, hbw, trow, lane0, warp0);
+                    if (after()) break;
+                } else {
+                    tmem_wait_st();                                                     // last iteration's messages are in place
+                    { float none[NDEG<0>]; layers<0>(softn, hbw, trow, mbar, ph, lane0, active, none); }
+                    if (after()) break;
+                }
             }
             if (!locked) ret = parity ? -iter : iter + 1;                               // :5424
 
             if (io.post) {
+                // PP: the column's result is in buffer (iterations run * column weight) mod 2, single copy
+                auto at = [&](int col) -> float {
+                    if constexpr (PP) return soft2[((done * s_cw[col]) & 1) * BUF + col * CS + pos_of(col, tid)];
+                    else return soft2[col * CS + tid + K::rt_ri()[col]];
+                };
                 if (io.post_dtype == 1) {
                     float* p = (float*)io.post + (size_t)f * N;
                     for (int col = 0; col < C; col++)
-                        if (ALL_ACTIVE || active) p[col * Z + tid] = soft2[col * CS + tid + K::rt_ri()[col]];
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = at(col);
                 } else {
                     double* p = (double*)io.post + (size_t)f * N;
                     for (int col = 0; col < C; col++)
-                        if (ALL_ACTIVE || active) p[col * Z + tid] = (double)soft2[col * CS + tid + K::rt_ri()[col]];
+                        if (ALL_ACTIVE || active) p[col * Z + tid] = (double)at(col);
                 }
             }
             // hb holds the packed decisions of the final posteriors (:5421).  Error counts are popcounts -- the
