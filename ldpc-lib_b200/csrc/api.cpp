@@ -162,6 +162,8 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
         CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream, h->dp.alpha));
     } else if (use_fast && h->decoder_id == LDPCB200_LMS_DEC) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);
+        if (const char* g = getenv("LDPCB200_GRID_PER_SM"))        // development: fewer resident CTAs per SM (latency experiments)
+            if (atoi(g) > 0) fgrid = std::min(fgrid, h->num_sms * atoi(g));
         CU(launch_lms_fast(h->fast, io, std::max(fgrid, 1), h->stream));
     } else if (use_fast && (h->decoder_id == LDPCB200_IMS_DEC || h->decoder_id == LDPCB200_MS_DEC)) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
@@ -363,7 +365,7 @@ int ldpcb200_info(ldpcb200_handle h, int* N, int* R, int* E, int* device)
 int ldpcb200_kernel_info(ldpcb200_handle h, int* fast, int* threads, int* frames_per_cta, int* ctas_per_sm, int* smem_bytes)
 {
     if (!h) return fail(LDPCB200_EINVAL, "null handle");
-    if (fast) *fast = h->fast.ok ? (1 + h->fast.variant) | (h->fast.tmem ? 16 : 0) : 0;
+    if (fast) *fast = h->fast.ok ? (1 + h->fast.variant) | (h->fast.tmem ? 16 : 0) | (h->fast.tmem == 2 ? 32 : 0) : 0;
     if (threads) *threads = h->fast.ok ? h->fast.threads : h->nt;
     if (frames_per_cta) *frames_per_cta = h->fast.ok ? h->fast.frames_per_cta : 1;
     if (ctas_per_sm) *ctas_per_sm = h->fast.ok ? h->fast.ctas_per_sm : h->grid / std::max(h->num_sms, 1);

@@ -305,12 +305,24 @@ cudaError_t launch_lms_spec_jit(const void* kernel, int zp, size_t smem, const F
 //               chosen when a frame's E*Z messages fit the 512 TMEM columns often enough to keep >= 12 warps on an SM
 size_t lms_tmem_smem_bytes(int b, int c, int Z, int maxdeg);
 size_t lms_tmem_pad_smem(size_t smem, int minb);
+size_t lms_tmem2_smem_bytes(int b, int c, int Z, int maxdeg);
 
 bool lms_spec_geometry(const QcHost& g, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant, bool allow_tmem)
 {
     if (g.E > 512 || g.Z > 1024 || g.maxdeg > MAXDEG_FAST) return false;
     *zp = (g.Z + 31) & ~31;
     const int hw = *zp / 32;
+    const char* t2 = getenv("LDPCB200_TMEM2");
+    if (allow_tmem && t2 && *t2 == '1' && g.Z % 32 == 0 && g.maxdeg <= 16 && g.c * hw < 1023 && 2 * g.E * ((hw + 3) / 4) <= 512 && hw >= 4) {
+        // two frames per CTA (lms_tmem2.cuh): one CTA per SM owns all the tensor memory it needs
+        const size_t need = lms_tmem2_smem_bytes(g.b, g.c, g.Z, g.maxdeg);
+        if (need <= (size_t)smem_per_block) {
+            *minb = 1;
+            *smem = need;
+            *variant = 3;
+            return true;
+        }
+    }
     if (allow_tmem && g.maxdeg <= 32 && g.c * hw < 1023) {
         int tcols = 32;
         while (tcols < g.E * ((hw + 3) / 4)) tcols *= 2;
@@ -355,16 +367,22 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
     const bool tmem = !(no_tmem && *no_tmem == '1');
     const char* no_aot = getenv("LDPCB200_NO_AOT");         // 1 (development): compile at run time even when an ahead-of-time instance exists
     int aot = -1;
+    bool two = false;
     if (!(no_spec && *no_spec == '1') && !(no_aot && *no_aot == '1' && allow_jit)) {
-        if (tmem) aot = find_lms_spec_aot(g, 3);            // messages in tensor memory (lms_tmem.cuh)
-        if (aot >= 0) p.tmem = 1;
-        else aot = find_lms_spec_aot(g, 0);
+        const char* t2 = getenv("LDPCB200_TMEM2");          // 1: two frames per CTA (lms_tmem2.cuh; measured slower) instead of one (lms_tmem.cuh)
+        if (tmem && t2 && *t2 == '1') aot = find_lms_spec_aot(g, 6);
+        if (aot >= 0) { p.tmem = 2; two = true; }
+        else if (tmem) {
+            aot = find_lms_spec_aot(g, 3);                  // messages in tensor memory (lms_tmem.cuh)
+            if (aot >= 0) p.tmem = 1;
+        }
+        if (aot < 0) aot = find_lms_spec_aot(g, 0);
     }
     if (aot >= 0) {                                          // a code-specialised instance exists for this matrix
         int minb = 1;
         lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);
         if (p.smem_bytes <= (size_t)smem_per_block) {
-            p.ok = 1; p.variant = 1; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.spec_index = aot;
+            p.ok = 1; p.variant = 1; p.frames_per_cta = two ? 2 : 1; p.ctas_per_sm = minb; p.spec_index = aot;
             return p;
         }
         p.tmem = 0;
@@ -376,9 +394,9 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
             std::string why;
             const void* k = lms_spec_jit(g, zp, minb, variant, 0, why);
             if (k) {
-                p.ok = 1; p.variant = 2; p.frames_per_cta = 1; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem;
+                p.ok = 1; p.variant = 2; p.frames_per_cta = variant == 3 ? 2 : 1; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem;
                 p.jit_kernel = k;
-                p.tmem = variant == 2;
+                p.tmem = variant == 3 ? 2 : variant == 2;
                 return p;
             }
             p.note = why;

@@ -9,6 +9,7 @@
 #include "channel.cuh"
 #include "lms_spec.cuh"
 #include "lms_tmem.cuh"
+#include "lms_tmem2.cuh"
 #include "ms_spec.cuh"
 #include "ms_tmem.cuh"
 
@@ -24,8 +25,18 @@ size_t lms_tmem_smem_bytes(int b, int c, int Z, int maxdeg)
     const bool pp = Z % 32 == 0;
     const size_t soft = pp ? 2 * (size_t)c * (Z + 32) : 2 * (size_t)c * Z, hb = (size_t)(c * hw > 3 ? c * hw : 3) + 1;
     const size_t plan = (size_t)((b * nb + 8 * nwarps - 1) / (8 * nwarps)) * ((maxdeg + 3) / 4) * zp;
-    const size_t mbar = (soft + hb + plan + zp + 1) & ~(size_t)1;     // + the quick-look word per thread
+    const size_t mbar = (soft + (pp ? 2 : 1) * hb + plan + zp + 1) & ~(size_t)1;     // + the quick-look word per thread
     return sizeof(float) * (mbar + 2 + 4 + (pp ? c : 0));
+}
+
+// shared memory of LmsTmem2<K> (lms_tmem2.cuh, SMEM_WORDS): two buffers of float2 posteriors | packed decisions x 2 | syndrome plan | misc | column weights
+size_t lms_tmem2_smem_bytes(int b, int c, int Z, int maxdeg)
+{
+    const int zp = (Z + 31) / 32 * 32, hw = zp / 32, nb = (Z + 31) / 32, nwarps = zp / 32;
+    const size_t soft = 4 * (size_t)c * (Z + 32), hb = (size_t)(c * hw > 3 ? c * hw : 3) + 1;
+    const size_t plan = (size_t)((b * nb + 8 * nwarps - 1) / (8 * nwarps)) * ((maxdeg + 3) / 4) * zp;
+    const size_t misc = (soft + 2 * hb + plan + zp + 1) & ~(size_t)1;
+    return sizeof(float) * (misc + 8 + c);
 }
 
 // shared memory of MsTmem<K, IS_INT> (ms_tmem.cuh, SMEM_WORDS)
@@ -47,7 +58,8 @@ size_t lms_tmem_pad_smem(size_t smem, int minb)
 struct SpecEntry {
     const char* name;
     const void* kernel;
-    int kind;                       // 0 LMS_DEC, 1 MS_DEC fp32, 2 IMS_DEC; 3 / 4 / 5 = LMS_DEC / MS_DEC / IMS_DEC with the messages in tensor memory
+    int kind;                       // 0 LMS_DEC, 1 MS_DEC fp32, 2 IMS_DEC; 3 / 4 / 5 = LMS_DEC / MS_DEC / IMS_DEC with the messages in tensor memory;
+                                    // 6 = LMS_DEC, tensor memory, two frames per CTA (lms_tmem2.cuh)
     int b, c, Z, E, zp, minb, maxdeg;
     const int *rp, *col, *sh;       // host copies for matching
 };
@@ -72,6 +84,7 @@ struct SpecRegistrar {
 #define LDPC_MS_SPEC_KIND_lmst 3
 #define LDPC_MS_SPEC_KIND_mst 4
 #define LDPC_MS_SPEC_KIND_imst 5
+#define LDPC_MS_SPEC_KIND_lmst2 6
 #define LDPC_MS_SPEC_REGISTER(KIND, NAME, B_, C_, Z_, E_, ZP_, MINB_)                                          \
     static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)KIND##_spec_##NAME, LDPC_MS_SPEC_KIND_##KIND, B_, C_, Z_, E_, ZP_, MINB_, ldpcb200::gen_##NAME::Code::MAXDEG, \
         ldpcb200::gen_##NAME::Code::RP, ldpcb200::gen_##NAME::Code::COL, ldpcb200::gen_##NAME::Code::SH});
@@ -105,12 +118,13 @@ void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size
     if (smem) {
         if (e.kind == 0) *smem = sizeof(float) * (2 * (size_t)e.c * e.Z + (e.c * hw > 4 ? e.c * hw : 4));
         else if (e.kind == 3) *smem = lms_tmem_smem_bytes(e.b, e.c, e.Z, e.maxdeg);
+        else if (e.kind == 6) *smem = lms_tmem2_smem_bytes(e.b, e.c, e.Z, e.maxdeg);
         else if (e.kind == 4 || e.kind == 5) *smem = ms_tmem_smem_bytes(e.c, e.Z, e.kind == 5);
         else *smem = ms_spec_smem_bytes(e.c, e.Z);
         // tensor-memory variant: exactly `minb` CTAs may share an SM (their TMEM columns add up to 512; one more
         // resident CTA would sit in tcgen05.alloc until another exits), so the request is padded until minb + 1
         // no longer fit into the 228 KB of an sm_100 SM
-        if (e.kind >= 3) *smem = lms_tmem_pad_smem(*smem, e.minb);
+        if (e.kind >= 3 && e.kind <= 5) *smem = lms_tmem_pad_smem(*smem, e.minb);
     }
 }
 

@@ -38,6 +38,12 @@
 #ifndef LMS_TMEM_FFMA2
 #define LMS_TMEM_FFMA2 0        // PP: the offset / scale FFMA of two edges as one fma.rn.f32x2
 #endif
+#ifndef LMS_TMEM_WHATIF
+#define LMS_TMEM_WHATIF 0       // development, WRONG RESULTS: 1 no barrier between block rows, 2 no minima, 3 no posterior stores, 4 no repeat stores
+#endif
+#ifndef LMS_TMEM_PP_BAL
+#define LMS_TMEM_PP_BAL 0       // PP: column k is stored rotated by k mod NWARPS warps, so the repeat stores spread over the warps
+#endif
 #ifndef LMS_TMEM_PP_BRANCH
 #define LMS_TMEM_PP_BRANCH 1    // PP: warp 0's repeat stores behind a branch (0: predicated stores in every warp)
 #endif
@@ -186,11 +192,17 @@ struct LmsTmem {
     static constexpr int CS = PP ? Z + 32 : 2 * Z;
     static constexpr int BUF = C * CS;                        // PP: word offset of the second buffer
     static constexpr int SOFT_WORDS = PP ? 2 * C * CS : C * CS;
+    // PP_BAL: the words of column k sit SEG(k) warps further (cyclically): lane n = 32w + l writes word 32 * ((w + SEG) mod NWARPS) + l,
+    // so the 32 repeated words of column k are the ones of warp (NWARPS - SEG(k)) mod NWARPS -- a different warp for every column
+    // of a block row instead of warp 0 for all of them (with warp 0 as the only one, every block row waited for it at its barrier)
+    static __host__ __device__ constexpr int SEG(int col) { return (LMS_TMEM_PP_BAL && PP) ? col % (ZP / 32) : 0; }
+    static __device__ __forceinline__ int seg_words(unsigned wu, int col) { return (int)((wu + (unsigned)SEG(col)) % (unsigned)(ZP / 32)) * 32; }
+    static __device__ __forceinline__ int phys(int col, int p) { int q = p + 32 * SEG(col); return q >= Z ? q - Z : q; }
     static constexpr int TCOLS = K::TCOLS;                    // power of two >= 32, >= E * ceil(warps / 4)
     static constexpr int NWARPS = ZP / 32;
     // shared memory (words): posteriors | packed decisions hb (+ one zero word) | syndrome plan | mbarrier (8-byte aligned) | misc
     static constexpr int HB_WORDS = (C * HW > 3 ? C * HW : 3) + 1;
-    static constexpr int PLAN_OFF = SOFT_WORDS + HB_WORDS;
+    static constexpr int PLAN_OFF = SOFT_WORDS + (PP ? 2 : 1) * HB_WORDS;      // PP: the decisions of two consecutive iterations
     static constexpr int PLAN_WORDS = ((B * NB + 8 * NWARPS - 1) / (8 * NWARPS)) * ((K::MAXDEG + 3) / 4) * ZP;
     static constexpr int PLAN1_OFF = PLAN_OFF + PLAN_WORDS;      // quick syndrome look (syndrome_quick): one word per thread
     static constexpr int MBAR_OFF = (PLAN1_OFF + ZP + 1) & ~1;
@@ -439,6 +451,12 @@ struct LmsTmem {
     // ---- PP block rows.  Compile-time bookkeeping of the two buffers of a column
     static __host__ __device__ constexpr int touch_index(int e) { int t = 0; for (int i = 0; i < e; i++) t += K::COL[i] == K::COL[e] ? 1 : 0; return t; }
     static __host__ __device__ constexpr int col_weight(int col) { int t = 0; for (int i = 0; i < E; i++) t += K::COL[i] == col ? 1 : 0; return t; }
+    // DELTA of the edge that reads what edge e writes (the next edge of the same column, cyclically)
+    static __host__ __device__ constexpr int next_delta(int e)
+    {
+        for (int i = 1; i <= E; i++) if (K::COL[(e + i) % E] == K::COL[e]) return K::DELTA[(e + i) % E];
+        return 0;
+    }
     // the buffer edge e reads in an iteration of parity PAR (it writes the other one)
     template <int PAR> static __host__ __device__ constexpr int rbuf(int e) { return (PAR * col_weight(K::COL[e]) + touch_index(e)) & 1; }
 
@@ -451,7 +469,7 @@ struct LmsTmem {
             if constexpr (Q < NDEG<J>) {
                 constexpr int e = K::RP[J < B ? J : 0] + Q;
                 if constexpr (K::EARLY[e] == WANT_EARLY) {
-                    constexpr int a = K::DELTA[e] / 32, b = K::DELTA[e] % 32;
+                    constexpr int a = (K::DELTA[e] / 32 + SEG(K::COL[e])) % NWARPS, b = K::DELTA[e] % 32;
                     constexpr int off = (rbuf<PAR>(e) * C + K::COL[e]) * CS + b;
                     sv[Q] = softl[uoff[a] + off];
                 }
@@ -460,17 +478,24 @@ struct LmsTmem {
         }
     }
     template <int J, int PAR, int Q = 0>
-    static __device__ __forceinline__ void pp_put(float* softn, unsigned* hbw, bool lane0, const float (&nv)[NDEG<J>])
+    static __device__ __forceinline__ void pp_put(float* softn, const float* softl, const unsigned (&uoff)[NWARPS], unsigned* hbw, bool lane0, const float (&nv)[NDEG<J>])
     {
         if constexpr (Q < NDEG<J>) {
             constexpr int e = K::RP[J] + Q;
             constexpr int off = ((rbuf<PAR>(e) ^ 1) * C + K::COL[e]) * CS;
-            softn[off] = nv[Q];                                                                  // one word per lane
+            if constexpr (SEG(K::COL[e]) == 0) softn[off] = nv[Q];                               // one word per lane
+            else const_cast<float*>(softl)[uoff[SEG(K::COL[e])] + off] = nv[Q];
+#if LMS_TMEM_PP_BAL
+            // the repeat: the warp whose words are 0 .. 31 of this column; not needed when the next reader's DELTA is a multiple of 32
+            if constexpr (next_delta(e) % 32 != 0) {
+                if (uoff[SEG(K::COL[e])] == 0) const_cast<float*>(softl)[off + Z] = nv[Q];
+            }
+#endif
             if constexpr (K::LAST[e]) {                                                          // see put_posterior
                 const unsigned w = __ballot_sync(0xffffffffu, nv[Q] < 0.0f);
                 if (lane0) hbw[K::COL[e] * HW] = w;
             }
-            pp_put<J, PAR, Q + 1>(softn, hbw, lane0, nv);
+            pp_put<J, PAR, Q + 1>(softn, softl, uoff, hbw, lane0, nv);
         }
     }
     template <int J, int PAR, int Q = 0>
@@ -584,14 +609,14 @@ struct LmsTmem {
 
     // msg / sv: the row's old messages (tcgen05.ld in flight) and the early posteriors, both issued by the previous block row;
     // msgn / svn: the same for the next one
-    template <int J, int PAR>
+    template <int J, int PAR, bool LOAD = true>
     static __device__ __forceinline__ void pp_layer(float* softn, const float* softl, const unsigned (&uoff)[NWARPS], unsigned* hbw, unsigned trow,
                                                     bool lane0, bool warp0, unsigned (&msg)[NDEG<J>], float (&sv)[NDEG<J>],
                                                     unsigned (&msgn)[NDEG<J + 1>], float (&svn)[NDEG<J + 1>])
     {
         constexpr int E0 = K::RP[J], DEG = NDEG<J>;
         float v[DEG], m[DEG], nv[DEG];
-        pp_load<J, PAR, false>(softl, uoff, sv);
+        if constexpr (LOAD) pp_load<J, PAR, false>(softl, uoff, sv);
         tmem_wait_ld<DEG>(msg);
 #pragma unroll
         for (int q = 0; q + 1 < DEG; q += 2)                                                     // :5152-5158, two edges per FADD2
@@ -600,7 +625,12 @@ struct LmsTmem {
         const unsigned sacc = sign_xor<DEG, 0, DEG>(v) & 0x80000000u;                            // see layer()
         const float rone = __uint_as_float(sacc | 0x3f800000u), rhalf = __fmul_rn(rone, 0.5f);
         const float nhalf = __fmul_rn(rhalf, -0.4f);
+#if LMS_TMEM_WHATIF == 2
+#pragma unroll
+        for (int q = 0; q < DEG; q++) m[q] = fabsf(v[(q + 1) % DEG]);
+#else
         min_of_others<DEG>(v, m, 32767.400390625f);
+#endif
 #if LMS_TMEM_FFMA2
         {
             float th[DEG];
@@ -622,8 +652,13 @@ struct LmsTmem {
         for (int q = 0; q + 1 < DEG; q += 2)                                                     // :5199-5204
             add_f32x2(nv[q], nv[q + 1], v[q], v[q + 1], __uint_as_float(msg[q]), __uint_as_float(msg[q + 1]));
         if constexpr (DEG & 1) nv[DEG - 1] = v[DEG - 1] + __uint_as_float(msg[DEG - 1]);
-        pp_put<J, PAR>(softn, hbw, lane0, nv);
-#if LMS_TMEM_PP_BRANCH
+#if LMS_TMEM_WHATIF == 3
+        softn[0] = nv[0];
+#else
+        pp_put<J, PAR>(softn, softl, uoff, hbw, lane0, nv);
+#endif
+#if LMS_TMEM_WHATIF == 3 || LMS_TMEM_WHATIF == 4 || LMS_TMEM_PP_BAL
+#elif LMS_TMEM_PP_BRANCH
         pp_repeat<J, PAR>((unsigned)__cvta_generic_to_shared(softn), warp0 ? 0u : 1u, nv);
 #else
         if (warp0) pp_repeat_plain<J, PAR>(softn, nv);
@@ -643,19 +678,36 @@ struct LmsTmem {
             unsigned msgn[NDEG<J + 1>];
             float svn[NDEG<J + 1>];
             pp_layer<J, PAR>(softn, softl, uoff, hbw, trow, lane0, warp0, msg, sv, msgn, svn);
+#if LMS_TMEM_WHATIF != 1
             __syncthreads();
+#endif
             pp_layers<J + 1, PAR>(softn, softl, uoff, hbw, trow, lane0, warp0, msgn, svn);
         }
     }
-    template <int PAR>
-    static __device__ __forceinline__ void pp_iteration(float* softn, const float* softl, const unsigned (&uoff)[NWARPS], unsigned* hbw, unsigned trow,
-                                                        bool lane0, bool warp0)
+    // One PP iteration.  The syndrome check of the decisions `hb_prev` (the previous iteration's, or the channel's) has
+    // not been made yet: its quick look (the full pass where there is no quick look) runs inside block row 0 and its
+    // CTA-wide OR rides on the barrier that ends block row 0, so the check costs its instructions and nothing else.
+    // Block row 0 is therefore speculative: it writes the OTHER buffer of its columns, the other set of packed decisions
+    // (hbw_next) and its messages; when verdict() says "stop" the state before it is still complete (the caller
+    // does not count the iteration).  verdict(unsatisfied) -> true: stop here.
+    template <int PAR, class F>
+    static __device__ __forceinline__ bool pp_iteration(float* softn, const float* softl, const unsigned (&uoff)[NWARPS], const unsigned* hb_prev,
+                                                        unsigned* hbw_next, const unsigned* plan, unsigned trow, bool lane0, bool warp0, int tid, F&& verdict)
     {
-        unsigned msg[NDEG<0>];
-        float sv[NDEG<0>];
+        unsigned msg[NDEG<0>], msgn[NDEG<1>];
+        float sv[NDEG<0>], svn[NDEG<1>];
         tmem_wait_st();                                                                          // last iteration's messages are in place
         tmem_ld_n<NDEG<0>>(trow, msg);
-        pp_layers<0, PAR>(softn, softl, uoff, hbw, trow, lane0, warp0, msg, sv);
+        pp_load<0, PAR, false>(softl, uoff, sv);
+        const unsigned part = SYN_QUICK ? quick_partial(hb_prev, plan, tid) : full_partial(hb_prev, plan, tid);
+        pp_layer<0, PAR, false>(softn, softl, uoff, hbw_next, trow, lane0, warp0, msg, sv, msgn, svn);
+        int bad = __syncthreads_or(part != 0);
+        if constexpr (SYN_QUICK) {
+            if (!bad) bad = __syncthreads_or(full_partial(hb_prev, plan, tid) != 0);             // rare: a (nearly) converged frame
+        }
+        if (verdict(bad)) { tmem_wait_ld<NDEG<1>>(msgn); return true; }
+        pp_layers<1, PAR>(softn, softl, uoff, hbw_next, trow, lane0, warp0, msgn, svn);
+        return false;
     }
 
     // ---- syndrome of the hard decisions on packed bits.  hb[col * HW + w] = signs of positions 32w..32w+31 of
@@ -666,7 +718,7 @@ struct LmsTmem {
         const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll 8
         for (int col = 0; col < C; col++) {
-            const int bit = (ALL_ACTIVE || tid < Z) ? soft2[col * CS + tid] < 0.0f : 0;
+            const int bit = (ALL_ACTIVE || tid < Z) ? soft2[col * CS + phys(col, tid)] < 0.0f : 0;
             const unsigned w = __ballot_sync(0xffffffffu, bit);
             if (lane == 0) hb[col * HW + warp] = w;
         }
@@ -738,7 +790,8 @@ struct LmsTmem {
     // converged nearly every look finds an unsatisfied check and the full pass is skipped.  The verdict "non-zero" is
     // exact; "zero" only means that syndrome() has to decide.
     static constexpr bool SYN_QUICK = K::MAXDEG <= 16 && SYN_NT > 2 * NWARPS;
-    static __device__ __forceinline__ int syndrome_quick(const unsigned* hb, const unsigned* plan, int tid)
+    // this thread's share of the quick look / of the full pass (non-zero: an unsatisfied check); the CTA-wide OR is the caller's
+    static __device__ __forceinline__ unsigned quick_partial(const unsigned* hb, const unsigned* plan, int tid)
     {
         unsigned acc = window(hb, plan[PLAN_WORDS + tid]);
 #pragma unroll
@@ -748,14 +801,10 @@ struct LmsTmem {
             const int lanes = Z - 32 * (t % NB);
             if (lanes < 32) acc &= (1u << lanes) - 1u;
         }
-        return __syncthreads_or(acc != 0);
+        return acc;
     }
-
-    static __device__ __forceinline__ int syndrome(const unsigned* hb, const unsigned* plan, int tid)
+    static __device__ __forceinline__ unsigned full_partial(const unsigned* hb, const unsigned* plan, int tid)
     {
-        if constexpr (SYN_QUICK) {
-            if (syndrome_quick(hb, plan, tid)) return 1;
-        }
         unsigned bad = 0;
 #pragma unroll
         for (int r = 0; r < SYN_ROUNDS; r++) {
@@ -773,7 +822,19 @@ struct LmsTmem {
             }
             bad |= acc;
         }
-        return __syncthreads_or(bad != 0);
+        return bad;
+    }
+    static __device__ __forceinline__ int syndrome_quick(const unsigned* hb, const unsigned* plan, int tid)
+    {
+        return __syncthreads_or(quick_partial(hb, plan, tid) != 0);
+    }
+
+    static __device__ __forceinline__ int syndrome(const unsigned* hb, const unsigned* plan, int tid)
+    {
+        if constexpr (SYN_QUICK) {
+            if (syndrome_quick(hb, plan, tid)) return 1;
+        }
+        return __syncthreads_or(full_partial(hb, plan, tid) != 0);
     }
 
     // position of bit k of block column col in the doubled column (first copy)
@@ -784,7 +845,7 @@ struct LmsTmem {
     }
     static __device__ __forceinline__ void put(float* soft2, int col, int k, float x)
     {
-        const int q = pos_of(col, k), p = col * CS + q;
+        const int q = phys(col, pos_of(col, k)), p = col * CS + q;
         soft2[p] = x;
         if (!PP || q < 32) soft2[p + Z] = x;
     }
@@ -819,7 +880,7 @@ struct LmsTmem {
             }
         }
         build_plan(plan, tid);
-        if (tid == 0) hb[HB_WORDS - 1] = 0u;
+        if (tid == 0) { hb[HB_WORDS - 1] = 0u; if (PP) hb[2 * HB_WORDS - 1] = 0u; }
         if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"((unsigned)NWARPS) : "memory");
 
         // tensor memory: one warp allocates TCOLS columns for the CTA and frees them at the end
@@ -892,7 +953,11 @@ struct LmsTmem {
                     for (int u = 0; u < 16; u++) {
                         const int col = c0 + u;
                         if (col < C) {
-                            if (act) { softn[col * CS] = x[u]; if (!PP || warp0) softn[col * CS + Z] = x[u]; }
+                            if constexpr (PP) {
+                                const int sw = seg_words(wu, col);
+                                soft2[col * CS + sw + (tid & 31)] = x[u];
+                                if (sw == 0) soft2[col * CS + Z + (tid & 31)] = x[u];
+                            } else if (act) { softn[col * CS] = x[u]; softn[col * CS + Z] = x[u]; }
                             const unsigned w = __ballot_sync(0xffffffffu, act && x[u] < 0.0f);   // the packed decisions of the
                             if (lane0) hbw[col * HW] = w;                                         // channel values, as pack() builds them
                         }
@@ -907,8 +972,11 @@ struct LmsTmem {
                         int k = tid + K::rt_rot()[col];
                         if (k >= Z) k -= Z;
                         const float x = (float)__ldcs(y + col * Z + k);
-                        softn[col * CS] = x;
-                        if (!PP || warp0) softn[col * CS + Z] = x;
+                        if constexpr (PP) {
+                            const int sw = seg_words(wu, col);
+                            soft2[col * CS + sw + (tid & 31)] = x;
+                            if (sw == 0) soft2[col * CS + Z + (tid & 31)] = x;
+                        } else { softn[col * CS] = x; softn[col * CS + Z] = x; }
                     }
                 }
             }
@@ -917,38 +985,46 @@ struct LmsTmem {
             __syncthreads();
 
             if (!packed) pack(soft2, hb, tid);
-            int parity = syndrome(hb, plan, tid);                                   // :5111-5115
-            int ret = 0, locked = 0, iter, done = 0;
-            if (!parity) { ret = 1; locked = 1; }
-            // One pass of the loop = one iteration (PP: two, so that the buffer every edge uses is a compile-time constant).
-            // With LDPCB200_NO_EARLY_EXIT every iteration and every syndrome check runs (worst-case timing); `ret` keeps
-            // the count at which the reference would have stopped.
-            auto after = [&](void) -> bool {                                            // -> stop
-                done++;
-                const int par = syndrome(hb, plan, tid);                                // :5281-5284
-                if (!locked) { parity = par; if (!par) { ret = iter + 1; locked = 1; } }
-                return !par && !noexit;
-            };
-            for (iter = 0; iter < io.maxiter; iter++) {
-                if (!parity && !noexit) break;                                          // :5119
-                if constexpr (PP) {
-                    pp_iteration<0>(softn, softl, uoff, hbw, trow, lane0, warp0);
-                    if (after()) break;
-                    if (++iter >= io.maxiter) break;
-                    pp_iteration<1>(softn, softl, uoff, hbw, trow, lane0, warp0);
-                    if (after()) break;
-                } else {
+            int ret = 0, locked = 0, iter = 0, done = 0, parity = 1, hsel = 0;
+            if constexpr (PP) {
+                // The check of the decisions after `iter` complete iterations (the channel values' for 0, :5111-5115; :5281-5284)
+                // is made inside block row 0 of the next iteration (pp_iteration); only the last one stands alone.  With
+                // LDPCB200_NO_EARLY_EXIT every iteration and every check runs (worst-case timing); `ret` keeps the count at
+                // which the reference would have stopped.
+                auto verdict = [&](int bad) -> bool {                                   // -> stop
+                    if (!locked) { parity = bad; if (!bad) { ret = iter == 0 ? 1 : iter; locked = 1; } }
+                    return !bad && !noexit;                                             // :5119
+                };
+                for (;;) {
+                    const unsigned* hb_prev = hb + hsel * HB_WORDS;
+                    unsigned* hbw_next = hbw + (hsel ^ 1) * HB_WORDS;
+                    if (iter >= io.maxiter) { verdict(syndrome(hb_prev, plan, tid)); break; }
+                    const bool stop = (iter & 1) ? pp_iteration<1>(softn, softl, uoff, hb_prev, hbw_next, plan, trow, lane0, warp0, tid, verdict)
+                                                 : pp_iteration<0>(softn, softl, uoff, hb_prev, hbw_next, plan, trow, lane0, warp0, tid, verdict);
+                    if (stop) break;
+                    iter++; done++; hsel ^= 1;
+                }
+                if (!locked) ret = -iter;                                               // :5424
+            } else {
+                parity = syndrome(hb, plan, tid);                                       // :5111-5115
+                if (!parity) { ret = 1; locked = 1; }
+                for (iter = 0; iter < io.maxiter; iter++) {
+                    if (!parity && !noexit) break;                                      // :5119
                     tmem_wait_st();                                                     // last iteration's messages are in place
                     { float none[NDEG<0>]; layers<0>(softn, hbw, trow, mbar, ph, lane0, active, none); }
-                    if (after()) break;
+                    done++;
+                    const int par = syndrome(hb, plan, tid);                            // :5281-5284
+                    if (!locked) { parity = par; if (!par) { ret = iter + 1; locked = 1; } }
+                    if (!par && !noexit) break;
                 }
+                if (!locked) ret = parity ? -iter : iter + 1;                           // :5424
             }
-            if (!locked) ret = parity ? -iter : iter + 1;                               // :5424
+            const unsigned* hbf = hb + hsel * HB_WORDS;                                 // the packed decisions of the result
 
             if (io.post) {
                 // PP: the column's result is in buffer (iterations run * column weight) mod 2, single copy
                 auto at = [&](int col) -> float {
-                    if constexpr (PP) return soft2[((done * s_cw[col]) & 1) * BUF + col * CS + pos_of(col, tid)];
+                    if constexpr (PP) return soft2[((done * s_cw[col]) & 1) * BUF + col * CS + phys(col, pos_of(col, tid))];
                     else return soft2[col * CS + tid + K::rt_ri()[col]];
                 };
                 if (io.post_dtype == 1) {
@@ -968,7 +1044,7 @@ struct LmsTmem {
                 const int lane = tid & 31;
                 int nerr = 0, nerr_info = 0;
                 for (int t = tid; t < ((C * HW + 31) & ~31); t += ZP) {
-                    const unsigned w = t < C * HW ? hb[t] : 0u;
+                    const unsigned w = t < C * HW ? hbf[t] : 0u;
                     const int pc = __popc(w);
                     nerr += pc;
                     if (t >= B * HW) nerr_info += pc;
@@ -987,7 +1063,7 @@ struct LmsTmem {
                             const int col = g / HW, k0 = 32 * (g - col * HW);
                             int start = k0 + K::rt_ri()[col];
                             if (start >= Z) start -= Z;
-                            const unsigned* hc = hb + col * HW;
+                            const unsigned* hc = hbf + col * HW;
                             const int i0 = start >> 5, i1 = i0 + 1 < HW ? i0 + 1 : 0;
                             out[g] = __funnelshift_r(hc[i0], hc[i1], start & 31);
                         }

@@ -108,7 +108,7 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
     o << "    static constexpr int B = " << g.b << ", C = " << g.c << ", Z = " << g.Z << ", E = " << g.E << ", ZP = " << zp << ", MINB = " << minb
       << ", MAXDEG = " << g.maxdeg << ";\n";
     // variant 0: doubled columns, all check state in registers; 1: single copy, sign/position words in shared memory;
-    // 2: doubled columns in the rotation of their last writer, c2v messages in tensor memory (lms_tmem.cuh)
+    // 2: columns in the rotation of their last writer, c2v messages in tensor memory (lms_tmem.cuh); 3: the same, two frames per CTA (lms_tmem2.cuh)
     o << "    static constexpr bool DOUBLED = " << (variant != 1 ? "true" : "false") << ", PS_SMEM = " << (variant != 1 ? "false" : "true") << ";\n";
     o << "    static constexpr int TCOLS = " << tcols << ";\n";
     put_array(o, "    static constexpr int DELTA", delta, g.E);
@@ -144,7 +144,7 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
     // kind 0: LMS_DEC (layered), 1: MS_DEC fp32 (flooding), 2: IMS_DEC (flooding, fixed point)
     if (kind == 0) {
         o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io)\n";
-        o << "{ ldpcb200::" << (variant == 2 ? "LmsTmem" : "LmsSpec") << "<ldpcb200::gen_jit::Code>::kernel(io); }\n";
+        o << "{ ldpcb200::" << (variant == 3 ? "LmsTmem2" : variant == 2 ? "LmsTmem" : "LmsSpec") << "<ldpcb200::gen_jit::Code>::kernel(io); }\n";
     } else {
         o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)\n";
         o << "{ ldpcb200::" << (variant == 2 ? "MsTmem" : "MsSpec") << "<ldpcb200::gen_jit::Code, " << (kind == 2 ? "true" : "false") << ">::kernel(io, sp); }\n";

@@ -145,6 +145,7 @@ class Decoder:
         _check(lib().ldpcb200_kernel_info(self._h, *[C.byref(x) for x in v]))
         d = dict(zip(("fast", "threads", "frames_per_cta", "ctas_per_sm", "smem_bytes"), [x.value for x in v]))
         d["tmem"] = bool(d["fast"] & 16)
+        d["two_frames"] = bool(d["fast"] & 32)
         d["fast"] &= 15
         d["name"] = {0: "generic (table-driven, state in %s)" % ("shared memory" if d["smem_bytes"] else "an L2-resident workspace"), 1: "lms_fast_kernel (table-driven, shared memory)",
                      2: "%s (code-specialised, ahead of time)", 3: "%s (code-specialised, NVRTC)"}.get(d["fast"], "?")
@@ -161,7 +162,7 @@ class Decoder:
         if d["fast"] == 1 and self.decoder_id == ASP_DEC:
             d["name"] = "asp_fast_kernel (table-driven, double, messages in tensor memory)"
         if "%s" in d["name"]:
-            d["name"] %= {LMS_DEC: "lms_tmem" if d["tmem"] else "lms_spec", MS_DEC: "ms_tmem<float>" if d["tmem"] else "ms_spec<float>", IMS_DEC: "ms_tmem<int>" if d["tmem"] else "ms_spec<int>"}.get(self.decoder_id, "spec")
+            d["name"] %= {LMS_DEC: ("lms_tmem2" if d["two_frames"] else "lms_tmem") if d["tmem"] else "lms_spec", MS_DEC: "ms_tmem<float>" if d["tmem"] else "ms_spec<float>", IMS_DEC: "ms_tmem<int>" if d["tmem"] else "ms_spec<int>"}.get(self.decoder_id, "spec")
         return d
 
     def post_dtype(self):

@@ -178,14 +178,12 @@ def test_bench_kernel_sass_uses_tensor_memory_and_stays_within_its_instruction_b
     assert len(ops) > 1000
     for needed in ("LDTM", "STTM", "FMNMX3", "FADD2", "FFMA"):
         assert needed in ops, needed
-    first, last = ops.index("LDTM"), len(ops) - 1 - ops[::-1].index("STTM")
-    body = ops[first:last + 1]                                        # the iterations (the frame load's staging array is stack)
-    assert "LDL" not in body and "STL" not in body                    # nothing spilled in the layers
     import json
     mix = json.loads(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_mix.py"), "128", "16", "8", "--json"], input=sass,
                                     capture_output=True, text=True, check=True).stdout)
     pe = mix["per_edge"]
-    assert pe["total"] <= 11.2 and pe["alu"] <= 4.5 and pe["shared_memory_wavefronts"] <= 2.5, pe
+    assert "LDL" not in mix["opcodes"] and "STL" not in mix["opcodes"]      # nothing spilled in the block rows
+    assert pe["total"] <= 11.2 and pe["alu"] <= 4.5 and pe["lsu"] <= 2.5, pe
     # bench.py's roofline block quotes the committed copy of this output: it must describe the object that was built
     committed = json.load(open(os.path.join(ROOT, "profiles", "sass_mix_lmst_spec_c2t.json")))
     for k, v in pe.items():

@@ -72,3 +72,28 @@ def test_tmem_lms_long_run_against_oracle(ldpc, po):
     want = po.orc_decode(po.LMS, hd, 256, llr, 10, dtype=np.float32)
     assert np.array_equal(got["iters"], want["iters"])
     assert np.array_equal(got["hard"], np.packbits(want["hard"], axis=1, bitorder="little").view(np.uint32)[:, :got["hard"].shape[1]])
+
+
+@pytest.mark.parametrize("code,Z,snr,maxiter", [("ref32x16_b", 256, 2.2, 10), ("c4_wifi_12x24", 128, 2.0, 7)])
+def test_two_frames_per_cta_kernel_equals_the_one_frame_kernel(ldpc, po, monkeypatch, code, Z, snr, maxiter):
+    """lms_tmem2.cuh (opt-in, LDPCB200_TMEM2=1: two frames per CTA in lock step, packed f32x2 arithmetic) against lms_tmem.cuh:
+    bitwise equal posteriors, decisions and iteration counts -- the slots finish at different iterations, take new frames
+    while the neighbour carries on, and an odd frame count leaves one slot empty at the end."""
+    hd, llr = _llr(code, Z, snr, 1201, 37)
+    monkeypatch.delenv("LDPCB200_TMEM2", raising=False)
+    with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=2) as d:
+        assert d.kernel_info()["tmem"] and not d.kernel_info()["two_frames"]
+        a = d.decode(llr, maxiter, want_post=True)
+    monkeypatch.setenv("LDPCB200_TMEM2", "1")
+    with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=2) as d:
+        assert d.kernel_info()["two_frames"], d.kernel_info()
+        b = d.decode(llr, maxiter, want_post=True)
+        fixed = d.decode(llr, maxiter, no_early_exit=True)
+        sim = d.simulate(snr, 999, maxiter, seed=3)
+    assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["hard"], b["hard"])
+    assert np.array_equal(a["post"].view(np.uint32), b["post"].view(np.uint32))
+    assert np.array_equal(fixed["iters"], a["iters"])
+    monkeypatch.delenv("LDPCB200_TMEM2", raising=False)
+    with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=2) as d:
+        sim1 = d.simulate(snr, 999, maxiter, seed=3)
+    assert sim == sim1                                                   # the fused channel + counters path

@@ -51,6 +51,14 @@ def main():
     llr = hard = iters = None
     first = None
     for v in args.variants:
+        os.environ.pop("LDPCB200_GRID_PER_SM", None)
+        os.environ.pop("LDPCB200_TMEM2", None)
+        if v == "t2" or v.startswith("t2,"):                        # "t2": two frames per CTA (lms_tmem2.cuh, run-time compiled); "t2,NAME=VALUE": with macros
+            os.environ["LDPCB200_TMEM2"] = "1"
+            v = "jit" if v == "t2" else v[3:]
+        if v.startswith("grid"):                                    # "grid1": the ahead-of-time kernel with one CTA per SM
+            os.environ["LDPCB200_GRID_PER_SM"] = v[4:]
+            v = "aot"
         if v == "aot":
             os.environ.pop("LDPCB200_NO_AOT", None)
             os.environ.pop("LDPCB200_JIT_DEFINES", None)

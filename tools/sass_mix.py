@@ -39,29 +39,52 @@ def parse(text):
 def mix(text, edges, blockrows=None, warps=8):
     ins = parse(text)
     first = next(i for i, x in enumerate(ins) if x[1] == "LDTM")
+    addr_all = {x[0]: i for i, x in enumerate(ins)}
+    # blocks behind a predicated forward branch: a loop with stores = warp 0's repeat stores (weight 1 / warps); a block with a
+    # barrier = the full syndrome pass after a clean quick look (once or twice per frame: weight 0)
+    weight = [1.0] * len(ins)
+    for i, (addr, op, pred, tgt) in enumerate(ins):
+        if op == "BRA" and pred and tgt in addr_all and i < addr_all[tgt] <= i + 600:
+            j = addr_all[tgt]
+            blk = ins[i + 1:j]
+            if any(x[1] == "STS" for x in blk) and any(x[1] == "BRA" and x[3] is not None and x[3] <= x[0] for x in blk):
+                for k in range(i + 1, j):
+                    weight[k] = min(weight[k], 1.0 / warps)
+            elif any(x[1] == "BAR" for x in blk):
+                for k in range(i + 1, j):
+                    weight[k] = 0.0
     if blockrows:
-        bars, end = 0, None
-        for i in range(first, len(ins)):
-            if ins[i][1] == "BAR":
-                bars += 1
-                if bars == blockrows:
-                    end = i
-                    break
-        if end is None:
-            raise SystemExit("fewer than %d BAR after the first LDTM" % blockrows)
+        # the iteration = the window [an LDTM, the BLOCKROWS-th unconditional BAR after it] that holds the most three-input minima
+        # (frame load and syndrome code also contain LDTM / BAR)
+        def window(start):
+            bars = 0
+            for i in range(start, len(ins)):
+                if ins[i][1] == "BAR" and weight[i] == 1.0:
+                    bars += 1
+                    if bars == blockrows:
+                        return i
+            return None
+        best = None
+        for i, x in enumerate(ins):
+            if x[1] != "LDTM" or (i > 0 and ins[i - 1][1] == "LDTM"):
+                continue
+            e = window(i)
+            if e is None:
+                continue
+            score = sum(1 for k in range(i, e + 1) if ins[k][1] in ("FMNMX3", "FMNMX", "HMNMX2", "VIMNMX") and weight[k] == 1.0)
+            if best is None or score > best[0]:
+                best = (score, i, e)
+        if best is None:
+            raise SystemExit("fewer than %d BAR after any LDTM" % blockrows)
+        first, end = best[1], best[2]
     else:
         last_sttm = max(i for i, x in enumerate(ins) if x[1] == "STTM")
         end = next(i for i in range(last_sttm, len(ins)) if ins[i][1] == "BAR")
     body = ins[first:end + 1]
-    addr_index = {x[0]: i for i, x in enumerate(body)}
-    warp0_only = [False] * len(body)
-    for i, (addr, op, pred, tgt) in enumerate(body):
-        if op == "BRA" and pred and tgt in addr_index and addr_index[tgt] > i:
-            j = addr_index[tgt]
-            blk = body[i + 1:j]
-            if any(x[1] == "STS" for x in blk) and any(x[1] == "BRA" and x[3] is not None and x[3] <= x[0] for x in blk):
-                for k in range(i + 1, j):
-                    warp0_only[k] = True
+    wbody = weight[first:end + 1]
+    warp0_only = [w < 1.0 and w > 0.0 for w in wbody]
+    body = [x for x, w in zip(body, wbody) if w > 0.0]
+    warp0_only = [f for f, w in zip(warp0_only, wbody) if w > 0.0]
 
     def group(op):
         return "alu" if op in ALU else "fma" if op in FMA else "lsu" if op in LSU else "tmem" if op in TMEM else "other"
