@@ -16,10 +16,12 @@ One JSON line on stdout (rank 0):
             loop): host parameter block in, noise + LLR generated inside the decoder's first load, host
             counters and per-frame records out (D2H inside the timed region), + the NCCL all-reduce of the
             counters when N > 1
-  roofline  HBM byte roofline of the decode kernel (it is instruction-issue bound; the issue
-            roofline is in "issue")
+  roofline  the binding roofline of the decode kernel (SURVEY.md 8d "the slower"): edge-update instruction rooflines
+            -- issue slots, ALU pipe, LSU pipe, shared-memory wavefronts -- from tracked tool outputs under profiles/
+            (static SASS mix of the built object, dynamic instruction count of the ncu capture); roofline_hbm is the
+            byte roofline (not binding: 3 %)
   cpu_baseline   the compiled reference (oracle/_ref) decoding a bounded sample of the same LLR buffers on
-            the host cores, and a parity check of the GPU results on that sample
+            the host cores (rank 0, at every N), and a parity check of the GPU results on that sample
 `--impl reference` times the unmodified reference bp_simulation() on all host cores instead.
 """
 import argparse
@@ -41,11 +43,30 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CODE, Z, SNR_DB, MAXITER, DECODER = "ref32x16_b", 256, 2.0, 10, 8      # 8 = LMS_DEC
 FRAMES_PER_GPU = 1 << 20
 METRIC, UNIT = "decoded_info_gbps_10iter", "Gbit/s"
-TRAFFIC_BYTES_PER_FRAME = (2148179000 + 14701312) / 65536        # ncu capture of the bench kernel (lmst_spec_c2t, v8): 33 003 B per frame
-# SASS instruction mix of one iteration of the bench kernel (tools/sass_mix.py on the built object; profiles/):
-# (ALU-pipe, total, shared-memory) instructions per edge update and lane
-SASS_MIX = {True: (4.10, 12.02, 3.20, "lms_tmem, min-of-others form (tools/sass_mix.py on lmst_spec_c2t; profiles/r01_lms_tmem_v8_ncu.txt)"),
-            False: (13.9, 25.6, None, "lms_spec (profiles/r01_lms_spec_v1_ncu.txt)")}
+
+
+def tracked(name):
+    """A tracked tool output under profiles/ (the roofline block quotes these instead of literals typed in here)."""
+    with open(os.path.join(ROOT, "profiles", name)) as f:
+        return json.load(f)
+
+
+def kernel_figures(info):
+    """Instructions per edge update of the kernel that runs, from tracked artefacts:
+    static  -- tools/sass_mix.py on the built object (profiles/sass_mix_lmst_spec_c2t.json; `make -C ldpc-lib_b200 sassmix`,
+               tests/test_abi.py fails when it no longer matches the build): one iteration's block rows;
+    dynamic -- smsp__inst_executed.sum of the ncu capture / warp-level edge updates (profiles/bench_kernel_ncu.json,
+               tools/ncu_kernel_json.py): everything the kernel executes, frame load, syndrome checks and outputs included."""
+    if not info.get("tmem") or info.get("two_frames"):
+        return None
+    mix, ncu = tracked("sass_mix_lmst_spec_c2t.json"), tracked("bench_kernel_ncu.json")
+    pe = mix["per_edge"]
+    return {"k_static": pe["total"], "alu_static": pe["alu"], "fma_static": pe["fma"], "lsu_static": pe["lsu"] + pe["tmem"],
+            "shared_wavefronts_static": pe["shared_memory_wavefronts"],
+            "k_dynamic": ncu["instructions_per_edge_update_dynamic"],
+            "shared_wavefronts_dynamic": ncu["shared_wavefronts_per_edge_update"],
+            "dram_bytes_per_frame": ncu["dram_bytes_per_frame"],
+            "sources": ["profiles/sass_mix_lmst_spec_c2t.json", "profiles/bench_kernel_ncu.json (" + ncu["source"] + ")"]}
 
 
 def load_binding():
@@ -60,6 +81,8 @@ def workload_config(n_gpus, frames):
     return {"workload": "C2: REF-32x16-B 16x32 Z=256 (N=8192,K=4096), LMS_DEC layered offset min-sum, max 10 iters, "
                         "BPSK/AWGN Eb/N0=2.0 dB, all-zero codeword",
             "frames_per_gpu_per_step": frames, "fixed_iterations": True,
+            "fixed_iterations_note": "every frame runs all 10 iterations AND the syndrome check of every iteration (none is skipped after "
+                                     "the first success); the reported iteration count is the one at which the reference would have stopped",
             "l2": "inputs (32 KiB/frame fp32 LLR, 32 GiB/GPU) larger than L2", "parallelism": "frames sharded x%d" % n_gpus}
 
 
@@ -290,13 +313,39 @@ def run_ours(args):
             peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "measured"
         except Exception:
             pass
-        sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-        edge_updates = frames * dec.E * Z * MAXITER / (kernel_ms * 1e-3)
-        issue_peak = 148 * 4 * 32 * sm_hz * 1e6                      # thread-instructions / s
-        alu_ops, all_ops, lsu_ops, mix_src = SASS_MIX[bool(info.get("tmem"))]
-        fr = {"alu_pipe": edge_updates * alu_ops / (148 * 64 * sm_hz * 1e6), "issue_slots": edge_updates * all_ops / issue_peak}
-        if lsu_ops:
-            fr["shared_memory_wavefronts"] = edge_updates * lsu_ops / (148 * 32 * sm_hz * 1e6)
+        sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        edge_updates = frames * dec.E * Z * MAXITER / (kernel_ms * 1e-3)               # thread-level edge updates / s
+        kf = kernel_figures(info)
+        issue_peak = 148 * 4 * 32 * sm_hz                                           # thread-instructions / s: 4 schedulers x 32 lanes per SM and clock
+        if kf:
+            # Per SM and clock: 4 x 32 thread-instructions issue; the ALU pipe takes 64 lanes; the LSU pipe (shared memory +
+            # tensor memory instructions) 32 lanes; shared memory one 32-lane wavefront.  Measured edge updates / s x the
+            # kernel's instructions per edge update against each; the binding roofline is the largest fraction.
+            fr = {"issue_slots": edge_updates * kf["k_dynamic"] / issue_peak,
+                  "alu_pipe": edge_updates * kf["alu_static"] / (148 * 64 * sm_hz),
+                  "lsu_pipe": edge_updates * kf["lsu_static"] / (148 * 32 * sm_hz),
+                  "shared_memory_wavefronts": edge_updates * kf["shared_wavefronts_dynamic"] / (148 * 32 * sm_hz)}
+            bound = max(fr, key=fr.get)
+            per_edge = {"issue_slots": kf["k_dynamic"], "alu_pipe": kf["alu_static"], "lsu_pipe": kf["lsu_static"],
+                        "shared_memory_wavefronts": kf["shared_wavefronts_dynamic"]}[bound]
+            peak_units = {"issue_slots": issue_peak, "alu_pipe": 148 * 64 * sm_hz, "lsu_pipe": 148 * 32 * sm_hz,
+                          "shared_memory_wavefronts": 148 * 32 * sm_hz}[bound]
+            roofline = {"bound": "issue" if bound == "issue_slots" else bound, "achieved": edge_updates * per_edge, "peak": peak_units,
+                        "unit": "thread-instructions/s" if bound != "shared_memory_wavefronts" else "lane-wavefronts/s",
+                        "frac": fr[bound], "fracs": fr, "k": kf["k_dynamic"], "k_static": kf["k_static"],
+                        "edge_updates_per_s": edge_updates, "per_edge_update": per_edge,
+                        "traffic": kf["dram_bytes_per_frame"] * frames, "sm_clock_mhz": sm_hz / 1e6,
+                        "k_at_100_gbps": issue_peak / (100e9 / K * dec.E * Z * MAXITER),
+                        "sources": kf["sources"],
+                        "note": "SURVEY.md 8d: the slower of the byte roofline and the edge-update instruction roofline; the byte roofline "
+                                "is in roofline_hbm"}
+            traffic = kf["dram_bytes_per_frame"] * frames
+        else:
+            roofline, traffic = None, None
+        roofline_hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                        "peak_source": peak_src, "bytes_per_frame": bytes_per_frame}
+        if roofline is None:
+            roofline = roofline_hbm
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world, frames),
@@ -314,20 +363,8 @@ def run_ours(args):
                                            "avg_iterations_rank0": r3["iter_sum"] / max(r3["frames"], 1),
                                            "fer_rank0": r3["frame_errors"] / max(r3["frames"], 1),
                                            "call": "ldpcb200_simulate, reference semantics (max 10 iterations, syndrome early exit)"},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": TRAFFIC_BYTES_PER_FRAME * frames, "peak_source": peak_src, "bytes_per_frame": bytes_per_frame,
-                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_lms_tmem_v8_ncu.txt (ncu --set full, "
-                                               "65536 frames) scaled to this launch"},
-                # the binding rooflines: min-sum is compare / logic / shared-memory work.  Per SM and clock:
-                # 4 x 32 thread-instructions issue, the ALU pipe takes 64 lanes, shared memory one 32-lane wavefront.
-                # Instructions per edge update of the kernel that ran (SASS_MIX above) x measured edge updates / s against
-                # each of the three; `frac` is the largest.
-                "issue": {"bound": max(fr, key=fr.get), "frac": max(fr.values()), "fracs": fr,
-                          "edge_updates_per_s": edge_updates, "alu_ops_per_edge_update": alu_ops,
-                          "instr_per_edge_update": all_ops, "shared_memory_ops_per_edge_update": lsu_ops, "source": mix_src,
-                          "alu_lane_peak_per_s": 148 * 64 * sm_hz * 1e6, "thread_instr_peak_per_s": issue_peak,
-                          "instr_per_edge_update_at_peak": issue_peak / edge_updates}}
-        if world == 1 and not args.no_cpu:
+                "roofline": roofline, "roofline_hbm": roofline_hbm}
+        if not args.no_cpu:                                          # rank 0, at every N: the reference beside the GPU figure in the same run
             line["cpu_baseline"] = cpu_baseline(dec, llr, hard, iters, K)
         emit(line)
     if world > 1:
