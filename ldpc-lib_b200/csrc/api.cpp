@@ -417,7 +417,17 @@ int ldpcb200_decode_batch(ldpcb200_handle h, const void* llr, int llr_dtype, int
     }
 
     // host buffers on at least one side: three-stage pipeline (H2D | decode | D2H) over chunks of
-    // frames, two slots, copies on their own streams
+    // frames, two slots, copies on their own streams.  Whatever way this function is left, no copy into a caller's
+    // buffer or a slot may still be in flight: the guard drains the three streams on the error paths too.
+    struct Drain {
+        ldpcb200_handle_s* h;
+        bool armed;
+        ~Drain()
+        {
+            if (!armed) return;
+            cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->s_out);
+        }
+    } drain{h, true};
     size_t per_frame_bytes = (size_t)N * esz + (size_t)nwords * 4 + (hard && !packed ? N : 0) + (posterior ? N * psz : 0) + (aux ? N * 2 : 0) + 8;
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_frames, ((size_t)192 << 20) / per_frame_bytes));
     if (chunk > 64) chunk &= ~63;
@@ -472,6 +482,7 @@ int ldpcb200_decode_batch(ldpcb200_handle h, const void* llr, int llr_dtype, int
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaStreamSynchronize(h->s_out));
     CU(cudaStreamSynchronize(h->s_in));
+    drain.armed = false;
     CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return 0;
 }

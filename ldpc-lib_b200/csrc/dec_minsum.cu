@@ -238,6 +238,7 @@ struct ImsGeneric {
             if (val > thr) val = thr;
             int ival = (int16_t)floor(val * max_quant / thr + 0.5);
             iy[i] = (int16_t)(sign ? -ival : ival);
+            soft[i] = iy[i];                                            // defined results when no iteration runs (maxiter == 0)
             if (io.aux) io.aux[(size_t)f * N + i] = iy[i];
         }
         for (int i = tid; i < R; i += nt) { min1[i] = 0; min2[i] = 0; ps[i] = 0; }

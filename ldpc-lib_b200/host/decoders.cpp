@@ -1,5 +1,7 @@
 #include "decoders.h"
 
+#include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,6 +84,14 @@ static int ensure_engine(DEC_STATE* st, double alpha, double thr, int qbits, int
     return make_engine(st);
 }
 
+// What the reference leaves in its caller-visible arrays, decoder by decoder:
+//   decword, decision == 0: 0 / 1; decision != 0: the soft output -- BP_DEC / SP_DEC soft[] itself (:1767, :1907, :1991, :2173),
+//     ASP_DEC the probabilities soft_out (make_output :2308, :2396, :2570), IASP_DEC soft_out / 2^16 (imake_output :3806),
+//     MS_DEC / LMS_DEC the posterior LLRs (:4670, :5413), IMS_DEC the integer posteriors (:5579-5589); TASP_DEC and LCHE_DEC
+//     ignore `decision` (:2736, lche_decod);
+//   soft[] (the input): BP_DEC / SP_DEC overwrite it with their posteriors; ASP_DEC / TASP_DEC replace it by the channel
+//     probabilities e^-y / (e^y + e^-y), y = clip(soft / 2, +-20) (:2351-2358, :2611-2618); IASP_DEC by 1 / (1 + e^clip(soft, +-20))
+//     (:3849-3854); the min-sum family and LCHE_DEC leave it alone.
 static int decode_one(DEC_STATE* st, int id, double soft[], double decword[], int maxiter, int decision,
                       double alpha = MS_ALPHA, double thr = MS_THR, int qbits = MS_QBITS, int dbits = MS_DBITS)
 {
@@ -89,19 +99,41 @@ static int decode_one(DEC_STATE* st, int id, double soft[], double decword[], in
     if (!ensure_engine(st, alpha, thr, qbits, dbits)) return -100000;
     const int n = st->n;
     std::vector<unsigned char> hard(n);
-    std::vector<double> post;
-    bool intdec = id == IMS_DEC || id == IASP_DEC;
-    // the reference leaves its posterior in soft[] for BP_DEC / SP_DEC (decoders.cpp:1738, 1949); decision != 0 asks for soft output
-    bool want_post = !intdec && (decision != 0 || id == BP_DEC || id == SP_DEC) && st->engine_precision == 64;
+    const bool soft_out = decision != 0 && id != TASP_DEC && id != LCHE_DEC;
+    const bool want_post = soft_out || id == BP_DEC || id == SP_DEC;
+    // the posterior comes in the engine's own type for this decoder (ldpcb200.h): int16 / uint16 for the fixed-point pair,
+    // float when the handle runs the fp32 kernels, else double
+    const bool f32 = (id == LMS_DEC || id == MS_DEC) && st->engine_precision == 32;
+    const int ptype = id == IMS_DEC ? LDPCB200_I16 : id == IASP_DEC ? LDPCB200_U16 : f32 ? LDPCB200_F32 : LDPCB200_F64;
+    std::vector<double> post;                                   // 8 bytes per value: large enough (and aligned) for every type
     if (want_post) post.resize(n);
     int32_t iters = 0;
     uint32_t flags = (id == BP_DEC && st->bp_chain) ? LDPCB200_BP_CHAIN_SYNDROME : 0;
     int rc = ldpcb200_decode_batch(st->engine, soft, LDPCB200_F64, 1, maxiter, flags, hard.data(), &iters,
-                                   want_post ? post.data() : NULL, LDPCB200_F64, NULL);
+                                   want_post ? (void*)post.data() : NULL, ptype, NULL);
     if (rc) { fprintf(stderr, "decode: %s\n", ldpcb200_last_error()); return -100000; }
-    if (decision == 0 || !want_post) for (int i = 0; i < n; i++) decword[i] = hard[i];
-    else for (int i = 0; i < n; i++) decword[i] = post[i];
-    if (want_post && (id == BP_DEC || id == SP_DEC)) memcpy(soft, post.data(), sizeof(double) * n);
+    if (want_post && ptype != LDPCB200_F64) {                   // widen in place, back to front
+        const void* raw = post.data();
+        for (int i = n - 1; i >= 0; i--)
+            post[i] = ptype == LDPCB200_I16 ? (double)((const int16_t*)raw)[i]
+                    : ptype == LDPCB200_U16 ? (double)((const uint16_t*)raw)[i] / 65536.0
+                    : (double)((const float*)raw)[i];
+    }
+    if (soft_out) for (int i = 0; i < n; i++) decword[i] = post[i];
+    else for (int i = 0; i < n; i++) decword[i] = hard[i];
+    if (id == BP_DEC || id == SP_DEC) memcpy(soft, post.data(), sizeof(double) * n);
+    else if (id == ASP_DEC || id == TASP_DEC) {
+        for (int i = 0; i < n; i++) {
+            const double x = soft[i] * 0.5, y = x > 20.0 ? 20.0 : x < -20.0 ? -20.0 : x;
+            const double e0 = exp(y), e1 = exp(-y);
+            soft[i] = e1 / (e0 + e1);
+        }
+    } else if (id == IASP_DEC) {
+        for (int i = 0; i < n; i++) {
+            const double x = soft[i], y = x > 20.0 ? 20.0 : x < -20.0 ? -20.0 : x;
+            soft[i] = 1.0 / (1.0 + exp(y));
+        }
+    }
     st->maxiter = maxiter;
     return iters;
 }

@@ -91,6 +91,21 @@ def ref_decode(dec, hd, Z, llr, maxiter, fresh=True, want_post=True):
     return dict(hard=hard, iters=iters, post=post, aux=aux)
 
 
+def ref_decode_arrays(dec, hd, Z, llr1, maxiter, decision):
+    """One call of the compiled reference decoder with the given `decision` on one frame: what it leaves in decword[] and
+    in its input array.  Returns dict(decword float64[N], soft_after float64[N], iter)."""
+    hd = _hd16(hd)
+    b, c = hd.shape
+    llr1 = np.ascontiguousarray(llr1, dtype=np.float64).reshape(-1)
+    N = c * Z
+    assert llr1.size == N
+    decword, after, it = np.zeros(N), np.zeros(N), C.c_int(0)
+    rc = ref().ref_decode_arrays(C.c_int(dec), _ptr(hd, C.c_short), b, c, Z, _ptr(llr1, C.c_double), maxiter, int(decision),
+                                 _ptr(decword, C.c_double), _ptr(after, C.c_double), C.byref(it))
+    assert rc == 0, rc
+    return dict(decword=decword, soft_after=after, iter=it.value)
+
+
 def orc_decode(dec, hd, Z, llr, maxiter, dtype=np.float64, chain=False, alpha=MS_ALPHA):
     """Run the C oracle's restatement of decoder `dec`.  dtype=float32 is available for LMS/MS."""
     hd = _hd16(hd)

@@ -40,8 +40,10 @@ DEC_STATE* open_state(int decoder_id, const short* hd, int b, int c, int M)
 }
 
 // same dispatch and same compile-time decoder parameters as bp_simulation.cpp:716-729
-int run_decoder(DEC_STATE* st, int id, int maxiter)
+int run_decoder(DEC_STATE* st, int id, int maxiter, int decision = DEC_DECISION)
 {
+#undef DEC_DECISION
+#define DEC_DECISION decision
     switch (id) {
     case BP_DEC:   return bp_decod_qc_lm(st, st->y, st->decword, maxiter, DEC_DECISION);
     case SP_DEC:   return sum_prod_decod_qc_lm(st, st->y, st->decword, maxiter, DEC_DECISION);
@@ -102,6 +104,22 @@ int ref_decode(int decoder_id, const short* hd, int b, int c, int M,
         if (fresh_state) { decod_close(st); st = NULL; }
     }
     if (st) decod_close(st);
+    return 0;
+}
+
+// The caller-visible arrays after ONE call with the given `decision` (fresh state): decword[N] as the decoder left it
+// (0 / 1 or soft values) and soft_after[N] = the input array st->y after the call (some decoders overwrite it).
+int ref_decode_arrays(int decoder_id, const short* hd, int b, int c, int M, const double* llr, int maxiter, int decision,
+                      double* decword, double* soft_after, int* iter)
+{
+    int N = c * M;
+    DEC_STATE* st = open_state(decoder_id, hd, b, c, M);
+    if (!st) return -1;
+    memcpy(st->y, llr, N * sizeof(double));
+    *iter = run_decoder(st, decoder_id, maxiter, decision);
+    memcpy(decword, st->decword, N * sizeof(double));
+    memcpy(soft_after, st->y, N * sizeof(double));
+    decod_close(st);
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // Uses the decoder interface exactly the way the reference's callers do (bp_simulation.cpp:353-382, 716-729):
 // decod_open -> fill st->hd -> decod_init -> copy LLRs into st->y -> call the decoder -> read st->decword.
-// argv: <decoder id> <b> <c> <M> <maxiter> <hd.bin int16> <llr.bin f64> <out.bin>; out = per frame: int32 iter + N bytes
+// argv: <decoder id> <b> <c> <M> <maxiter> <hd.bin int16> <llr.bin f64> <out.bin> [decision]; out = per frame: int32 iter + N bytes,
+// or with decision given: int32 iter + N doubles decword + N doubles = the input array after the call
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -8,7 +9,10 @@
 
 int main(int argc, char** argv)
 {
-    if (argc != 9) return 2;
+    if (argc != 9 && argc != 10) return 2;
+    const int decision = argc == 10 ? atoi(argv[9]) : DEC_DECISION;
+#undef DEC_DECISION
+#define DEC_DECISION decision
     int id = atoi(argv[1]), b = atoi(argv[2]), c = atoi(argv[3]), M = atoi(argv[4]), maxiter = atoi(argv[5]);
     std::vector<short> hd((size_t)b * c);
     FILE* f = fopen(argv[6], "rb");
@@ -39,9 +43,14 @@ int main(int argc, char** argv)
         case LCHE_DEC: iter = lche_decod(st, st->y, st->decword, maxiter, DEC_DECISION); break;
         default: return 7;
         }
-        for (int i = 0; i < n; i++) bits[i] = st->decword[i] != 0.0;
         fwrite(&iter, 4, 1, out);
-        fwrite(bits.data(), 1, n, out);
+        if (argc == 10) {
+            fwrite(st->decword, sizeof(double), n, out);
+            fwrite(st->y, sizeof(double), n, out);
+        } else {
+            for (int i = 0; i < n; i++) bits[i] = st->decword[i] != 0.0;
+            fwrite(bits.data(), 1, n, out);
+        }
     }
     fclose(in); fclose(out);
     decod_close(st);

@@ -44,6 +44,38 @@ def test_decoders_h_interface_matches_reference_golden(po, compat_bin, tmp_path,
     assert np.array_equal(np.packbits(hard, axis=1), G[key + "_hard"])
 
 
+@pytest.mark.parametrize("dec", ["BP", "SP", "ASP", "MS", "IMS", "IASP", "TASP", "LMS", "LCHE"])
+def test_decision_argument_and_input_side_effects_match_the_reference(po, compat_bin, tmp_path, dec):
+    """decision != 0: decword carries what the reference puts there (its soft output; TASP_DEC and LCHE_DEC ignore the
+    argument), and the input array is left as the reference leaves it (posteriors for BP / SP, channel probabilities for
+    ASP / TASP / IASP, untouched for the min-sum family and LCHE) -- against the compiled reference, call by call."""
+    if not po.have_ref():
+        pytest.skip("oracle/_ref not built")
+    G = np.load(os.path.join(ROOT, "tests", "golden", "decoders_c4_z27.npz"))
+    hd, Z, llr = G["hd"], int(G["Z"]), G["llr"]
+    did = getattr(po, dec)
+    maxiter = int(G["maxiter"])
+    N = llr.shape[1]
+    hd.astype(np.int16).tofile(tmp_path / "hd.bin")
+    for f in (0, 5):
+        llr[f:f + 1].tofile(tmp_path / "llr.bin")
+        subprocess.check_call([compat_bin, str(did), str(hd.shape[0]), str(hd.shape[1]), str(Z), str(maxiter),
+                               str(tmp_path / "hd.bin"), str(tmp_path / "llr.bin"), str(tmp_path / "out.bin"), "1"])
+        raw = np.fromfile(tmp_path / "out.bin", np.uint8)
+        it = int(raw[:4].view(np.int32)[0])
+        decword, after = raw[4:4 + 8 * N].view(np.float64), raw[4 + 8 * N:].view(np.float64)
+        want = po.ref_decode_arrays(did, hd, Z, llr[f], maxiter, 1)
+        assert it == want["iter"]
+        if dec in ("MS", "IMS", "IASP", "LMS", "TASP", "LCHE"):        # exact arithmetic, or 0 / 1
+            assert np.array_equal(decword, want["decword"]), dec
+        else:                                                            # exp / log: libm vs CUDA
+            assert np.allclose(decword, want["decword"], rtol=1e-9, atol=1e-12), dec
+        if dec in ("BP", "SP"):
+            assert np.allclose(after, want["soft_after"], rtol=1e-9, atol=1e-12)
+        else:
+            assert np.array_equal(after, want["soft_after"]), dec
+
+
 def wilson(k, n, z=1.96):
     p = k / n
     d = 1 + z * z / n

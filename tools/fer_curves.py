@@ -42,8 +42,17 @@ REF_C1 = {"snr": [1.0, 1.25, 1.5, 1.75, 2.0, 2.25, 2.5],
           "TASP": [0.373, 0.0899, 0.0457, 0.0263, 0.0182, 0.0113, 0.00735],
           "LMS": [0.769, 0.427, 0.158, 0.0734, 0.0478, 0.0263, 0.0170]}
 
-# (label, code, Z, decoder, precision, maxiter, snrs, frame errors, max frames, reference curve or None)
+# (label, code, Z, decoder, precision, maxiter, snrs, frame errors, max frames, reference curve or None[, modulation, punctured blocks])
 RUNS = [
+    # BASELINE config 4 as written: BP flooding vs layered, FER down to 1e-6 (>= 30 frame errors per point), 8 GPUs
+    ("C4F LMS_DEC 20it (layered)", "c4_wifi_12x24", 81, "LMS_DEC", 32, 20, [2.0, 2.25, 2.5, 2.75], 100, 400000000, None),
+    ("C4F TASP_DEC 20it (layered)", "c4_wifi_12x24", 81, "TASP_DEC", 64, 20, [1.75, 2.0, 2.25, 2.5], 100, 200000000, None),
+    ("C4F BP_DEC 20it (flooding)", "c4_wifi_12x24", 81, "BP_DEC", 64, 20, [2.0, 2.25, 2.5, 2.75, 3.0], 60, 120000000, None),
+    ("C4F ASP_DEC 20it (flooding)", "c4_wifi_12x24", 81, "ASP_DEC", 64, 20, [2.0, 2.25, 2.5, 2.75, 3.0], 60, 120000000, None),
+    ("C4G TASP_DEC 20it (layered)", "c4_wifi_12x24", 81, "TASP_DEC", 64, 20, [2.75, 3.0, 3.25, 3.5], 60, 300000000, None),
+    ("C4G ASP_DEC 20it (flooding)", "c4_wifi_12x24", 81, "ASP_DEC", 64, 20, [3.25, 3.5], 60, 300000000, None),
+    # BASELINE config 3 as written: BG1-shaped Z = 384, QAM-64 demodulation fused with layered min-sum, 8 GPUs
+    ("C3 LMS_DEC 10it QAM-64 punct 2", "c3_bg1_46x68", 384, "LMS_DEC", 32, 10, [0.5, 0.75, 1.0, 1.5], 200, 3000000, None, 3, 2),
     ("C1 TASP_DEC 50it", "ref32x16_b", 126, "TASP_DEC", 64, 50, REF_C1["snr"], 400, 400000, REF_C1["TASP"]),
     ("C1 LMS_DEC 50it", "ref32x16_b", 126, "LMS_DEC", 32, 50, REF_C1["snr"], 2000, 4000000, REF_C1["LMS"]),
     ("C4 LMS_DEC 20it (layered)", "c4_wifi_12x24", 81, "LMS_DEC", 32, 20, [1.0, 1.5, 2.0, 2.25, 2.5, 2.75, 3.0], 200, 300000000, None),
@@ -71,7 +80,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
         group = dist.group.WORLD
     fixed = int(os.environ.get("FIXED_FRAMES", "0"))
-    for label, code, Z, dec, prec, maxiter, snrs, nerr, nmax, ref in RUNS:
+    for run in RUNS:
+        label, code, Z, dec, prec, maxiter, snrs, nerr, nmax, ref = run[:10]
+        mod, punct = (run[10], run[11]) if len(run) > 10 else (0, 0)
         if only and only not in label:
             continue
         hd, _ = load_code(code)
@@ -81,10 +92,11 @@ def main():
         with L.Decoder(hd, Z, getattr(L, dec), precision=prec, use_fast=2, device=local) as d:
             for k, snr in enumerate(snrs):
                 t0 = time.perf_counter()
-                ber, fer, r = SH.bp_simulation(d, maxiter, nerr, nmax, snr, 1.0, seed=1, stream=k, round_frames=1 << 14, max_round_frames=1 << 20,
-                                               group=group, device=device)
+                ber, fer, r = SH.bp_simulation(d, maxiter, nerr, nmax, snr, 1.0, modulation=mod, punctured_blocks=punct, seed=1, stream=k,
+                                               round_frames=1 << 14, max_round_frames=1 << 20, group=group, device=device)
+                secs = time.perf_counter() - t0
                 pt = {"snr_db": snr, "fer": fer, "ber": ber, "frames": r.experiment, "frame_errors": r.nde, "undetected": r.nue,
-                      "seconds": round(time.perf_counter() - t0, 2)}
+                      "seconds": round(secs, 2), "info_gbps_all_gpus": r.decoded * d.K / secs / 1e9}
                 if ref:
                     lo, hi = wilson(50, 50 / ref[k])
                     mylo, myhi = wilson(r.nde, r.experiment)
@@ -94,8 +106,13 @@ def main():
                     print(label, pt, file=sys.stderr)
             out.append({"case": label, "kernel": d.kernel_info()["name"], "points": pts})
     if rank == 0:
-        print(json.dumps({"runs": out, "n_gpus": world,
-                          "note": "stop rule: n frame errors or the frame budget, applied in frame order (simhost.frame_loop)"}, indent=1))
+        txt = json.dumps({"runs": out, "n_gpus": world,
+                          "note": "stop rule: n frame errors or the frame budget, applied in frame order (simhost.frame_loop)"}, indent=1)
+        if len(sys.argv) > 2:                    # libraries print banners on stdout (NCCL): a file keeps the JSON clean
+            with open(sys.argv[2], "w") as f:
+                f.write(txt + "\n")
+        else:
+            print(txt)
     if world > 1:
         dist.destroy_process_group()
 
