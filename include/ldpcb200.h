@@ -172,6 +172,12 @@ int ldpcb200_modulate(int Q, int ns, const uint8_t* bits, double* out, int devic
 /* sigma / sigmaQAM of bp_simulation.cpp:444-449 (host arithmetic, no device needed). */
 double ldpcb200_sigma(int b, int c, int punctured_blocks, double snr_db, int modulation);
 
+/* Girth, ACE spectrum and cycle spectrum of a base matrix, as the reference's driver computes them before every
+ * simulation (main_simulation.cpp:148-205 trace_matrix -> trace_pm.cpp:58 trace_bound_pol_mon_pm with GMAX = 20):
+ * *girth = shortest cycle length, ace[k] / spectrum[k] = ACE value and number of protograph cycles of the k-th
+ * shortest cycle length present, k < gtarget (the driver uses GTARGET = 4).  Host arithmetic, no device needed. */
+int ldpcb200_girth_spectrum(const int16_t* hd, int b, int c, int Z, int gtarget, int* girth, int* ace, int* spectrum);
+
 /* Diagnostic: generate and compile (NVRTC, no device needed) the code-specialised LMS_DEC kernel for a matrix
  * and target architecture sm_<major><minor>; *cubin_bytes = size of the result. */
 int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int sm_minor, int* cubin_bytes);

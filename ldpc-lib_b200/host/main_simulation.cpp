@@ -7,8 +7,8 @@
 // below TARGET_ERR (:543-571), the result descriptor and its keys (:588-616, appended to the result
 // file), the progress table (:621-633), and the optional marking loop that re-labels the non-(-1)
 // entries column by column from `{ data = array {...} min_modulo = n }` records (:66-119, 635-664).
-// Not reproduced: the girth / ACE spectrum print before every SNR point (trace_matrix, :496 -- display
-// only): girth_, girth_ACE and girth_spectrum are written as zeros.  GF(q)
+// The girth / ACE / cycle spectrum of every simulated matrix (trace_matrix, :496) comes from ldpcb200_girth_spectrum
+// (csrc/girth.cpp), once per matrix instead of once per SNR point; girth_, girth_ACE and girth_spectrum are written.  GF(q)
 // codes (_q_mod > 2) are refused.
 #include <cmath>
 #include <cstdio>
@@ -139,7 +139,8 @@ int main_simulation(int argc, char* argv[])
         bool mark_flag = mark_file != DEFAULT_MARKING;
         if (mark_flag && (fp = fopen(mark_file.c_str(), "rt")) == NULL) mark_flag = false;
 
-        int mark_num = -1, best_mark = -1, best_snr_idx = s_max;
+        int mark_num = -1, best_mark = -1, best_snr_idx = s_max, curr_girth = 0;
+        matrix<int> traced_HM;
         double best_err = 1.0, curr_BER = 1.0, curr_FER = 1.0;
         do {
             int s;
@@ -151,6 +152,23 @@ int main_simulation(int argc, char* argv[])
                     printf("code #%d, marked matrix #%d is being processed, SNR = %6.3f\n", code_idx, mark_num, snrs[s]);
                 EsN0[s] = snrs[s] + 10.0 * log10(2.0 * bitrate);
                 reset_random();                                   // all codes are tested with the same noise
+                if (q_mod <= 2) {
+                    // girth / ACE / cycle spectrum of the matrix about to be simulated (trace_matrix + show_matrix_property,
+                    // :496-497).  The reference recomputes it for every SNR point (1.8 s each at E = 128); it only depends on
+                    // the matrix, so it is computed when the matrix changes.
+                    if (!(traced_HM == current_HM)) {
+                        std::vector<int16_t> hd16((size_t)rows * columns);
+                        for (int i = 0; i < rows; i++)
+                            for (int j = 0; j < columns; j++) hd16[(size_t)i * columns + j] = (int16_t)current_HM(i, j);
+                        if (ldpcb200_girth_spectrum(hd16.data(), rows, columns, tailbite_length, GTARGET, &curr_girth, ACE.data(), girth_spectrum.data()))
+                            die("girth spectrum: bad matrix");
+                        traced_HM = current_HM;
+                    }
+                    printf("girth: %3d, ACE: ", curr_girth);
+                    for (int i = 0; i < GTARGET; i++) printf("%3d ", ACE[i]);
+                    printf(",  SPEC: ");
+                    for (int i = 0; i < GTARGET; i++) printf("%5d ", girth_spectrum[i]);
+                }
                 std::pair<double, double> result = bp_simulation(q_mod, current_HM, coef, 0, tailbite_length, num_iterations,
                                                                  num_frame_errors, num_experiments, snrs[s], best_errors[s], decoder_type,
                                                                  modulation_type, permutation_type, permutation_block, permutation_inter,
@@ -193,7 +211,7 @@ int main_simulation(int argc, char* argv[])
                 descriptor.open("column_weights").set(column_weights);
                 descriptor.open("row_weights").set(row_weights_write);
                 descriptor.open("girth").set(girth);
-                descriptor.open("girth_").set(0);
+                descriptor.open("girth_").set(curr_girth);
                 descriptor.open("girth_ACE").set(ACE);
                 descriptor.open("girth_spectrum").set(girth_spectrum);
                 descriptor.open("config_index").set(config_index);

@@ -244,6 +244,15 @@ class Decoder:
         return lib().ldpcb200_stream(self._h)
 
 
+def girth_spectrum(hd, Z, gtarget=4):
+    """Girth, ACE spectrum and cycle spectrum of a base matrix (host code; main_simulation.cpp:148-205) -> (girth, ace, spectrum)."""
+    hd = np.ascontiguousarray(hd, dtype=np.int16)
+    g = C.c_int()
+    ace, spec = np.zeros(gtarget, np.int32), np.zeros(gtarget, np.int32)
+    _check(lib().ldpcb200_girth_spectrum(_ptr(hd), hd.shape[0], hd.shape[1], Z, gtarget, C.byref(g), _ptr(ace), _ptr(spec)))
+    return g.value, [int(x) for x in ace], [int(x) for x in spec]
+
+
 def jit_check(hd, Z, sm=(10, 0)):
     """Generate + NVRTC-compile the code-specialised LMS_DEC kernel for a matrix (needs no GPU); -> cubin size."""
     hd = np.ascontiguousarray(hd, dtype=np.int16)

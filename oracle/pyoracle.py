@@ -106,6 +106,20 @@ def ref_decode_arrays(dec, hd, Z, llr1, maxiter, decision):
     return dict(decword=decword, soft_after=after, iter=it.value)
 
 
+def ref_girth(hd, Z, gtarget=4):
+    """The compiled reference's trace_bound_pol_mon_pm() as its driver calls it -> (girth, ACE[gtarget], spectrum[gtarget])
+    exactly as main_simulation.cpp:148-205 derives them."""
+    H = np.ascontiguousarray(hd, dtype=np.int32)
+    b, c = H.shape
+    S, SA = np.zeros(20, np.int32), np.zeros(20, np.int32)
+    rc = ref().ref_girth(_ptr(H, C.c_int), b, c, Z, gtarget, _ptr(S, C.c_int), _ptr(SA, C.c_int))
+    assert rc == 0
+    girth = next((g for g in range(1, 21) if S[g - 1]), 21)
+    ace = [int(x) for x in SA[girth - 1:] if x][:gtarget]
+    spec = [int(x) for x in S[girth - 1:] if x][:gtarget]
+    return girth, ace + [0] * (gtarget - len(ace)), spec + [0] * (gtarget - len(spec))
+
+
 def orc_decode(dec, hd, Z, llr, maxiter, dtype=np.float64, chain=False, alpha=MS_ALPHA):
     """Run the C oracle's restatement of decoder `dec`.  dtype=float32 is available for LMS/MS."""
     hd = _hd16(hd)

@@ -24,6 +24,7 @@
 #include "bp_simulation.h"
 #include "commons_portable.h"
 #include "data_structures.h"
+#include "trace_pm.h"
 
 namespace {
 
@@ -120,6 +121,23 @@ int ref_decode_arrays(int decoder_id, const short* hd, int b, int c, int M, cons
     memcpy(decword, st->decword, N * sizeof(double));
     memcpy(soft_after, st->y, N * sizeof(double));
     decod_close(st);
+    return 0;
+}
+
+// trace_bound_pol_mon_pm() as main_simulation.cpp:148-205 (trace_matrix) calls it: S[20] cycle counts, SA[20] ACE.
+int ref_girth(const int* H, int b, int c, int M, int gtarget, int* S, int* SA)
+{
+    int minACE[GMAX], maxACEspec[GMAX];
+    for (int i = 0; i < GMAX; i++) { S[i] = 0; SA[i] = 0; minACE[i] = 0; maxACEspec[i] = 100000000; }
+    ARRAY matr;
+    matr.ndim = 2;
+    put_nrow(&matr, b);
+    put_ncol(&matr, c);
+    put_addr(&matr, Alloc2d_int(b, c));
+    for (int i = 0; i < b; i++)
+        for (int j = 0; j < c; j++) matr.addr[i][j] = H[i * c + j];
+    trace_bound_pol_mon_pm(matr, M, GMAX, gtarget, S, SA, minACE, maxACEspec);
+    free(matr.addr);
     return 0;
 }
 
