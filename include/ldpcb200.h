@@ -12,6 +12,8 @@
  *   the nine binary *_decod* functions decoders.h:296-305     ldpcb200_decode_batch (1..n frames)
  *   Demodulate                         modulation.h:115       ldpcb200_demodulate
  *   QAM_modulator                      modulation.h:111       ldpcb200_modulate
+ *   Permutations_Open / _Init / Permutation                   ldpcb200_interleaver_tables,
+ *       direct_inverse_perm.cpp:139, :312, :785               ldpcb200_set_interleaver
  *   bp_simulation's frame loop         bp_simulation.cpp:591-824
  *       (noise -> LLR -> puncture -> decode -> count)         ldpcb200_simulate
  *
@@ -177,6 +179,22 @@ double ldpcb200_sigma(int b, int c, int punctured_blocks, double snr_db, int mod
  * *girth = shortest cycle length, ace[k] / spectrum[k] = ACE value and number of protograph cycles of the k-th
  * shortest cycle length present, k < gtarget (the driver uses GTARGET = 4).  Host arithmetic, no device needed. */
 int ldpcb200_girth_spectrum(const int16_t* hd, int b, int c, int Z, int gtarget, int* girth, int* ace, int* spectrum);
+
+/* Bit interleaver tables of the simulation path: Permutations_Open / Permutation_Init / Permutation,
+ * direct_inverse_perm.cpp:139, :312-782, :785-896 with the LCG myrand :131-135, as bp_simulation.cpp:417-425 opens them.
+ * modulation = enum ldpcb200_modulation (decides the bits per PAM component mode 2 deals the block columns to), mode =
+ * the scenario's permutation_type 0..4, block / inter = permutation_block / permutation_inter.  direct[j] = codeword bit
+ * sent at transmitted position j (Permutation direction 0, :573), inverse[i] = transmitted position that feeds decoder
+ * input i (direction 1, :684); N = c*Z entries each.  LDPCB200_EUNSUPPORTED where the reference's parameters do not
+ * define a permutation of the N positions (it would read stale memory).  Host arithmetic, no device needed. */
+int ldpcb200_interleaver_tables(const int16_t* hd, int b, int c, int Z, int modulation, int mode, int block, int inter,
+                                int32_t* direct, int32_t* inverse);
+
+/* Attach an interleaver to a handle: from then on ldpcb200_simulate / ldpcb200_generate_llr feed decoder input i with
+ * the LLR received at transmitted position inverse[i] (a gather / scatter inside the decoder's first load; puncturing
+ * is applied after it, bp_simulation.cpp:697-710).  direct / inverse: host arrays of N entries, mutually inverse
+ * permutations (checked); both NULL removes the interleaver. */
+int ldpcb200_set_interleaver(ldpcb200_handle h, const int32_t* direct, const int32_t* inverse);
 
 /* Diagnostic: generate and compile (NVRTC, no device needed) the code-specialised LMS_DEC kernel for a matrix
  * and target architecture sm_<major><minor>; *cubin_bytes = size of the result. */

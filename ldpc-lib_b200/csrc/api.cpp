@@ -94,7 +94,8 @@ struct ldpcb200_handle_s {
     int device = 0, num_sms = 0, smem_per_sm = 0, smem_per_block = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf tables, ws, counters, next, bpsynd, coef;
+    DevBuf tables, ws, counters, next, bpsynd, coef, perm;
+    bool has_perm = false;                  // perm holds direct[N] | inverse[N] (ldpcb200_set_interleaver)
     size_t ws_stride = 0, smem_ws = 0;      // smem_ws != 0: the table-driven kernel keeps its state in shared memory
     int grid = 0, nt = 0;
     Slot slot[2];
@@ -202,6 +203,7 @@ void fill_channel(const ldpcb200_handle_s* h, const ldpcb200_sim_params* sp, Cha
     ch.seed = sp->seed;
     ch.stream = sp->stream;
     ch.first_frame = sp->first_frame;
+    if (h->has_perm) { ch.perm_dir = (const int*)h->perm.p; ch.perm_inv = (const int*)h->perm.p + g.N; }
 }
 
 int check_sim(const ldpcb200_handle_s* h, const ldpcb200_sim_params* sp)
@@ -342,7 +344,7 @@ int ldpcb200_destroy(ldpcb200_handle h)
         if (s.ev_k) cudaEventDestroy(s.ev_k);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
     }
-    h->tables.release(); h->ws.release(); h->counters.release(); h->next.release(); h->bpsynd.release(); h->coef.release();
+    h->tables.release(); h->ws.release(); h->counters.release(); h->next.release(); h->bpsynd.release(); h->coef.release(); h->perm.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -552,6 +554,25 @@ int ldpcb200_generate_llr(ldpcb200_handle h, const ldpcb200_sim_params* sp, void
         CU(cudaMemcpyAsync((char*)llr + (size_t)f0 * N * esz, s.llr.p, (size_t)nf * N * esz, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
+    return 0;
+}
+
+int ldpcb200_set_interleaver(ldpcb200_handle h, const int32_t* direct, const int32_t* inverse)
+{
+    if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (!direct && !inverse) { h->has_perm = false; return 0; }
+    if (!direct || !inverse) return fail(LDPCB200_EINVAL, "direct and inverse must both be given (or both NULL)");
+    const int N = h->g.N;
+    for (int i = 0; i < N; i++)
+        if (inverse[i] < 0 || inverse[i] >= N || direct[inverse[i]] != i) return fail(LDPCB200_EINVAL, "direct / inverse are not mutually inverse permutations (entry %d)", i);
+    for (int j = 0; j < N; j++)
+        if (direct[j] < 0 || direct[j] >= N || inverse[direct[j]] != j) return fail(LDPCB200_EINVAL, "direct / inverse are not mutually inverse permutations (entry %d)", j);
+    DeviceGuard guard(h->device);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(h->perm.reserve(sizeof(int32_t) * 2 * (size_t)N));
+    CU(cudaMemcpy(h->perm.p, direct, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy((int32_t*)h->perm.p + N, inverse, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
+    h->has_perm = true;
     return 0;
 }
 

@@ -152,14 +152,25 @@ __device__ __forceinline__ void pam_demod(double x, double N0, double T, int m, 
     }
 }
 
-// Four consecutive BPSK / QAM-4 LLRs 4*i4 .. 4*i4+3 from ONE Philox block (bit-identical to channel_llr() of each bit;
-// the per-bit form computes the block four times over).  Punctured positions get the puncturing value.
-__device__ __forceinline__ void channel_llr4_bpsk(const ChannelParams& ch, unsigned long long frame, int i4, float out[4])
+// The decoder input that transmitted position j feeds (inverse permutation of bp_simulation.cpp:684, as a scatter)
+__device__ __forceinline__ int channel_dest(const ChannelParams& ch, int j)
+{
+    return ch.perm_dir ? __ldg(ch.perm_dir + j) : j;
+}
+
+// The BPSK / QAM-4 LLRs of the four consecutive transmitted positions 4*i4 .. 4*i4+3 from ONE Philox block (bit-identical
+// to channel_llr() of each bit; the per-bit form computes the block four times over).  dst[b] is the decoder input the
+// value belongs to (the position itself without an interleaver); punctured inputs get the puncturing value
+// (bp_simulation.cpp:697-710 overwrites y[] AFTER the inverse permutation).
+__device__ __forceinline__ void channel_llr4_bpsk(const ChannelParams& ch, unsigned long long frame, int i4, float out[4], int dst[4])
 {
     float z[4];
     channel_noise4(ch, frame, (unsigned int)i4, z);
 #pragma unroll
-    for (int b = 0; b < 4; b++) out[b] = (4 * i4 + b >= ch.punct_start) ? ch.punct_value : bpsk_llr(ch, z[b]);
+    for (int b = 0; b < 4; b++) {
+        dst[b] = channel_dest(ch, 4 * i4 + b);
+        out[b] = (dst[b] >= ch.punct_start) ? ch.punct_value : bpsk_llr(ch, z[b]);
+    }
 }
 
 // QAM-16/64/256 LLR of bit i (kept out of line: it is heavy in registers and only used by C3-like runs)
@@ -179,8 +190,9 @@ static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, un
 }
 
 // All m/2 LLRs carried by one PAM component (cidx = 2 * symbol + component) of a QAM-16/64/256 frame: one noise
-// sample, one pass through pam_demod.  out[b] is the LLR of bit (cidx / 2) * m + (cidx & 1) * m/2 + b; the
-// caller applies the puncturing.  Bit-identical to channel_llr_qam() bit by bit.
+// sample, one pass through pam_demod.  out[b] is the LLR of transmitted position (cidx / 2) * m + (cidx & 1) * m/2 + b;
+// the caller maps it to its decoder input (channel_dest) and applies the puncturing.  Bit-identical to
+// channel_llr_qam() bit by bit.
 static __device__ __noinline__ void channel_llr_qam_component(const ChannelParams& ch, unsigned long long frame, int cidx, float out[4])
 {
     const int half = ch.m >> 1;
@@ -191,10 +203,12 @@ static __device__ __noinline__ void channel_llr_qam_component(const ChannelParam
     for (int b = 0; b < 4; b++) out[b] = b < half ? (float)(-o[b]) : 0.0f;
 }
 
-// Channel LLR (log P0/P1, the decoder-side sign) of bit i of frame f for the all-zero codeword.
+// Channel LLR (log P0/P1, the decoder-side sign) of decoder input i of frame f for the all-zero codeword: the value
+// received at transmitted position perm_inv[i] (bp_simulation.cpp:684).
 __device__ __forceinline__ float channel_llr(const ChannelParams& ch, unsigned long long frame, int i)
 {
     if (i >= ch.punct_start) return ch.punct_value;
+    if (ch.perm_inv) i = __ldg(ch.perm_inv + i);
     if (ch.m <= 2) return bpsk_llr(ch, channel_noise(ch, frame, (unsigned int)i));
     return channel_llr_qam(ch, frame, i);
 }

@@ -18,6 +18,10 @@ struct ChannelParams {
     unsigned long long seed;
     unsigned int stream;
     unsigned long long first_frame;
+    // bit interleaver (direct_inverse_perm.cpp; bp_simulation.cpp:573, :684), device tables of N entries or null for the
+    // identity: perm_dir[j] = decoder input fed by transmitted position j, perm_inv[i] = transmitted position of input i
+    const int* perm_dir;
+    const int* perm_inv;
 };
 
 // Everything one decode launch reads and writes (all pointers are device pointers).

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
                     channel_llr_qam_component(io.ch, frame, c, o);
                     const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
                     for (int b = 0; b < half; b++) {
-                        const int i = i0 + b, col = i / Z, k = i - col * Z;
+                        const int i = channel_dest(io.ch, i0 + b), col = i / Z, k = i - col * Z;
                         const float x = i >= io.ch.punct_start ? io.ch.punct_value : o[b];
                         soft2[col * 2 * Z + k] = x; soft2[col * 2 * Z + Z + k] = x;
                     }
@@ -182,15 +182,16 @@ __global__ void __launch_bounds__(512) lms_fast_kernel(const __grid_constant__ L
             } else {
                 for (int i4 = tid; i4 < N / 4; i4 += nt) {                            // one Philox block -> four LLRs
                     float o[4];
-                    channel_llr4_bpsk(io.ch, frame, i4, o);
+                    int d[4];
+                        channel_llr4_bpsk(io.ch, frame, i4, o, d);
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        const int i = 4 * i4 + b, col = i / Z, k = i - col * Z;
+                        const int i = d[b], col = i / Z, k = i - col * Z;
                         soft2[col * 2 * Z + k] = o[b]; soft2[col * 2 * Z + Z + k] = o[b];
                     }
                 }
-                for (int i = (N & ~3) + tid; i < N; i += nt) {
-                    const int col = i / Z, k = i - col * Z;
+                for (int j = (N & ~3) + tid; j < N; j += nt) {
+                    const int i = channel_dest(io.ch, j), col = i / Z, k = i - col * Z;
                     const float x = channel_llr(io.ch, frame, i);
                     soft2[col * 2 * Z + k] = x; soft2[col * 2 * Z + Z + k] = x;
                 }

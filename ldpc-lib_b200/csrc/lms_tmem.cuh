@@ -915,22 +915,23 @@ struct LmsTmem {
                         channel_llr_qam_component(io.ch, frame, c, o);
                         const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
                         for (int b = 0; b < half; b++) {
-                            const int i = i0 + b, col = i / Z, k = i - col * Z;
+                            const int i = channel_dest(io.ch, i0 + b), col = i / Z, k = i - col * Z;
                             put(soft2, col, k, i >= io.ch.punct_start ? io.ch.punct_value : o[b]);
                         }
                     }
                 } else {
                     for (int i4 = tid; i4 < N / 4; i4 += ZP) {                        // one Philox block -> four LLRs
                         float o[4];
-                        channel_llr4_bpsk(io.ch, frame, i4, o);
+                        int d[4];
+                        channel_llr4_bpsk(io.ch, frame, i4, o, d);
 #pragma unroll
                         for (int b = 0; b < 4; b++) {
-                            const int i = 4 * i4 + b, col = i / Z, k = i - col * Z;
+                            const int i = d[b], col = i / Z, k = i - col * Z;
                             put(soft2, col, k, o[b]);
                         }
                     }
-                    for (int i = (N & ~3) + tid; i < N; i += ZP) {                    // tail when N is not a multiple of 4
-                        const int col = i / Z, k = i - col * Z;
+                    for (int j = (N & ~3) + tid; j < N; j += ZP) {                    // tail when N is not a multiple of 4
+                        const int i = channel_dest(io.ch, j), col = i / Z, k = i - col * Z;
                         put(soft2, col, k, channel_llr(io.ch, frame, i));
                     }
                 }

@@ -335,17 +335,18 @@ struct LmsTmem2 {
                     channel_llr_qam_component(io.ch, frame, c, o);
                     const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
                     for (int b = 0; b < half; b++) {
-                        const int i = i0 + b, col = i / Z, k = i - col * Z;
+                        const int i = channel_dest(io.ch, i0 + b), col = i / Z, k = i - col * Z;
                         store_pos(sw, (par * s_cw[col]) & 1, col, T::pos_of(col, k), s, i >= io.ch.punct_start ? io.ch.punct_value : o[b]);
                     }
                 }
             } else {
                 for (int i4 = tid; i4 < N / 4; i4 += ZP) {                        // one Philox block -> four LLRs
                     float o[4];
-                    channel_llr4_bpsk(io.ch, frame, i4, o);
+                    int d[4];
+                        channel_llr4_bpsk(io.ch, frame, i4, o, d);
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        const int i = 4 * i4 + b, col = i / Z, k = i - col * Z;
+                        const int i = d[b], col = i / Z, k = i - col * Z;
                         store_pos(sw, (par * s_cw[col]) & 1, col, T::pos_of(col, k), s, o[b]);
                     }
                 }

@@ -241,16 +241,20 @@ struct MsSpec {
                         float o[4];
                         channel_llr_qam_component(io.ch, frame, c, o);
                         const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
-                        for (int b = 0; b < half; b++) y[i0 + b] = i0 + b >= io.ch.punct_start ? io.ch.punct_value : o[b];
+                        for (int b = 0; b < half; b++) {
+                            const int i = channel_dest(io.ch, i0 + b);
+                            y[i] = i >= io.ch.punct_start ? io.ch.punct_value : o[b];
+                        }
                     }
                 } else {
                     for (int i4 = tid; i4 < N / 4; i4 += ZP) {                        // one Philox block -> four LLRs
                         float o[4];
-                        channel_llr4_bpsk(io.ch, frame, i4, o);
+                        int d[4];
+                        channel_llr4_bpsk(io.ch, frame, i4, o, d);
 #pragma unroll
-                        for (int b = 0; b < 4; b++) y[4 * i4 + b] = o[b];
+                        for (int b = 0; b < 4; b++) y[d[b]] = o[b];
                     }
-                    for (int i = (N & ~3) + tid; i < N; i += ZP) y[i] = channel_llr(io.ch, frame, i);
+                    for (int j = (N & ~3) + tid; j < N; j += ZP) { const int i = channel_dest(io.ch, j); y[i] = channel_llr(io.ch, frame, i); }
                 }
             } else if (io.llr_dtype == 1) {
                 const float* src = (const float*)io.llr + (size_t)f * N;

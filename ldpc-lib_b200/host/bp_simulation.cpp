@@ -66,7 +66,7 @@ bp_simulation_stats const& bp_simulation_last_stats() { return g_stats; }
 std::pair<double, double> bp_simulation(
     int q_mod, matrix<int> const& H, matrix<int>& /*coef_matrix*/, int /*ncols2convert*/, int tailbite_length,
     int max_iterations, int n_frame_errors, int n_experiments, double snr, double reference_frame_error,
-    int decoder_type, int modulation_type, int permutation_type, int /*permutation_block*/, int /*permutation_inter*/,
+    int decoder_type, int modulation_type, int permutation_type, int permutation_block, int permutation_inter,
     int punctured_blocks, int show_process)
 {
     const int b = H.n_rows(), c = H.n_cols(), M = tailbite_length;
@@ -74,16 +74,6 @@ std::pair<double, double> bp_simulation(
     if (q_mod != 2) die("bp_simulation: q_mod = %d: GF(q) codes are outside the B200 engine (binary decoders only)", q_mod);
     if (modulation_type < MODULATION_SKIP || modulation_type > MODULATION_QAM256) die("Unknown modulation type: %d", modulation_type);
     if (permutation_type < 0 || permutation_type > 4) die("Unknown permutation type: %d", permutation_type);
-    if (permutation_type != 0) {
-        // The reference interleaves the (all-zero, bp_simulation.cpp:567) codeword, adds noise and de-interleaves
-        // the LLRs (:573, :684).  With one bit per channel use (no modulation, QAM-4) the LLRs are i.i.d., so the
-        // de-interleaved vector has the same distribution whatever the permutation: every interleaver mode gives the
-        // statistics of the identity, and puncturing is applied after de-interleaving (:697-710).  With QAM-16/64/256 the
-        // bit positions of a symbol differ in reliability and the permutation matters: not implemented.
-        if (modulation_type > MODULATION_QAM4)
-            die("bp_simulation: permutation_type = %d with modulation_type = %d: bit interleavers for QAM-16/64/256 are not implemented",
-                permutation_type, modulation_type);
-    }
     switch (decoder_type) {
     case BP_DEC: case SP_DEC: case ASP_DEC: case MS_DEC: case IMS_DEC: case IASP_DEC: case TASP_DEC: case LMS_DEC: case LCHE_DEC: break;
     default: die("Unknown decoder type: %d", decoder_type);
@@ -130,6 +120,20 @@ std::pair<double, double> bp_simulation(
         eng_hd = hd; memcpy(eng_key, key, sizeof key); eng_devs = de ? de : "";
     }
     const int G = (int)eng.size();
+
+    // Bit interleaver (bp_simulation.cpp:417-425): the reference interleaves the (all-zero, :567) codeword, modulates, adds
+    // noise, demodulates and de-interleaves the LLRs (:573, :684) before puncturing (:697-710).  The engine does the
+    // de-interleaving inside the decoder's first load from the same index tables (csrc/interleaver.cpp).
+    if (permutation_type != 0) {
+        std::vector<int32_t> dir((size_t)n), inv((size_t)n);
+        int rc = ldpcb200_interleaver_tables(hd.data(), b, c, M, modulation_type, permutation_type, permutation_block, permutation_inter, dir.data(), inv.data());
+        if (rc) die("bp_simulation: permutation_type = %d (block %d, inter %d) does not define a permutation of the %d code bits%s",
+                    permutation_type, permutation_block, permutation_inter, n, rc == LDPCB200_EUNSUPPORTED ? " (the reference would read stale memory)" : "");
+        for (auto h : eng)
+            if (ldpcb200_set_interleaver(h, dir.data(), inv.data())) die("bp_simulation: cannot attach the interleaver: %s", ldpcb200_last_error());
+    } else {
+        for (auto h : eng) ldpcb200_set_interleaver(h, NULL, NULL);
+    }
 
     ensure_random_is_initialized();
 #ifdef LDPCB200_WITH_REFERENCE_HEADERS

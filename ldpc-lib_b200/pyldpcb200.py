@@ -78,6 +78,9 @@ def lib():
         L.ldpcb200_modulate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.ldpcb200_jit_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.ldpcb200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.ldpcb200_girth_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ldpcb200_interleaver_tables.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]
+        L.ldpcb200_set_interleaver.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -235,6 +238,16 @@ class Decoder:
         _check(lib().ldpcb200_generate_llr(self._h, C.byref(sp), _ptr(out), dt))
         return out
 
+    def set_interleaver(self, direct=None, inverse=None):
+        """Attach (or with no arguments remove) a bit interleaver: simulate() / generate_llr() then feed decoder input i with the
+        LLR received at transmitted position inverse[i] (bp_simulation.cpp:684)."""
+        if direct is None and inverse is None:
+            _check(lib().ldpcb200_set_interleaver(self._h, None, None))
+            return
+        d, i = np.ascontiguousarray(direct, dtype=np.int32), np.ascontiguousarray(inverse, dtype=np.int32)
+        assert d.shape == (self.N,) and i.shape == (self.N,)
+        _check(lib().ldpcb200_set_interleaver(self._h, _ptr(d), _ptr(i)))
+
     def last_kernel_ms(self):
         ms, n = C.c_float(), C.c_int()
         _check(lib().ldpcb200_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
@@ -242,6 +255,15 @@ class Decoder:
 
     def stream(self):
         return lib().ldpcb200_stream(self._h)
+
+
+def interleaver_tables(hd, Z, modulation, mode, block=1, inter=1):
+    """Index tables of the reference's bit interleaver modes 0-4 (direct_inverse_perm.cpp) -> (direct[N], inverse[N])."""
+    hd = np.ascontiguousarray(hd, dtype=np.int16)
+    N = hd.shape[1] * Z
+    d, i = np.zeros(N, np.int32), np.zeros(N, np.int32)
+    _check(lib().ldpcb200_interleaver_tables(_ptr(hd), hd.shape[0], hd.shape[1], Z, modulation, mode, block, inter, _ptr(d), _ptr(i)))
+    return d, i
 
 
 def girth_spectrum(hd, Z, gtarget=4):

@@ -106,6 +106,18 @@ def ref_decode_arrays(dec, hd, Z, llr1, maxiter, decision):
     return dict(decword=decword, soft_after=after, iter=it.value)
 
 
+def ref_permutation(hd, Z, modulation, mode, block=1, inter=1):
+    """The compiled reference's interleaver tables (Permutations_Open / Permutation_Init / Permutation on index ramps):
+    (direct[N], inverse[N]); modulation as in bp_simulation (0 none, 1 QAM-4, 2 QAM-16, 3 QAM-64, 4 QAM-256)."""
+    hd = _hd16(hd)
+    b, c = hd.shape
+    QAM, half = [(1, 1), (4, 1), (16, 2), (64, 3), (256, 4)][modulation]
+    d, i = np.zeros(c * Z, np.int32), np.zeros(c * Z, np.int32)
+    rc = ref().ref_permutation(_ptr(hd, C.c_short), b, c, Z, QAM, half, mode, block, inter, _ptr(d, C.c_int), _ptr(i, C.c_int))
+    assert rc == 0
+    return d, i
+
+
 def ref_girth(hd, Z, gtarget=4):
     """The compiled reference's trace_bound_pol_mon_pm() as its driver calls it -> (girth, ACE[gtarget], spectrum[gtarget])
     exactly as main_simulation.cpp:148-205 derives them."""

@@ -124,6 +124,28 @@ int ref_decode_arrays(int decoder_id, const short* hd, int b, int c, int M, cons
     return 0;
 }
 
+// The reference's interleaver as bp_simulation.cpp:417-425, 573, 684 uses it, applied to index ramps: direct[j] = index of the
+// input element that Permutation(direction 0) puts at j, inverse[i] likewise for direction 1; -1 where nothing is written.
+int ref_permutation(const short* hd, int b, int c, int M, int QAM, int halfmlog, int mode, int block, int step, int* direct, int* inverse)
+{
+    PERMSTATE* st = Permutations_Open(b, c, M, QAM, halfmlog, mode, block, step);
+    if (!st) return -1;
+    std::vector<short*> rows(b);
+    std::vector<short> flat(hd, hd + (size_t)b * c);
+    for (int i = 0; i < b; i++) rows[i] = flat.data() + (size_t)i * c;
+    Permutation_Init(st, rows.data());
+    int N = c * M;
+    std::vector<double> in(N + N), out(N + N, -1.0);
+    for (int i = 0; i < N; i++) in[i] = i;
+    Permutation(st, 0, in.data(), out.data());
+    for (int i = 0; i < N; i++) direct[i] = (int)out[i];
+    std::fill(out.begin(), out.end(), -1.0);
+    Permutation(st, 1, in.data(), out.data());
+    for (int i = 0; i < N; i++) inverse[i] = (int)out[i];
+    Permutations_Close(st);
+    return 0;
+}
+
 // trace_bound_pol_mon_pm() as main_simulation.cpp:148-205 (trace_matrix) calls it: S[20] cycle counts, SA[20] ACE.
 int ref_girth(const int* H, int b, int c, int M, int gtarget, int* S, int* SA)
 {

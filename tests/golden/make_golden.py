@@ -98,6 +98,23 @@ JSONX_CASES = [("basic.jsonx", ""), ("matrices.jsonx", ""), ("refs_main.jsonx", 
 JSONX_DIES = [("refs_main.jsonx", "settings/fallback_only"), ("refs_main.jsonx", "nothing"), ("basic.jsonx", "alpha/x")]
 
 
+INTERLEAVER_CASES = [("c4_wifi_12x24", 27, 0, 1, 1, 1), ("c4_wifi_12x24", 27, 3, 1, 1, 1), ("c4_wifi_12x24", 27, 2, 2, 1, 1),
+                     ("c4_wifi_12x24", 27, 3, 2, 1, 1), ("c4_wifi_12x24", 27, 4, 2, 1, 1), ("c4_wifi_12x24", 27, 3, 3, 96, 1),
+                     ("c4_wifi_12x24", 27, 3, 3, 100, 1), ("c4_wifi_12x24", 27, 2, 4, 1, 12), ("ref32x16_b", 21, 3, 2, 1, 1),
+                     ("ref32x16_b", 21, 4, 2, 1, 1), ("ref32x16_b", 21, 2, 2, 1, 1), ("c3_bg1_46x68", 8, 3, 2, 1, 1)]
+
+
+def interleaver():
+    """The reference's interleaver tables (Permutations_Open / Permutation_Init / Permutation on index ramps)."""
+    out = {"cases": np.array([c[1:] for c in INTERLEAVER_CASES], np.int32), "codes": np.array([c[0] for c in INTERLEAVER_CASES])}
+    for k, (code, Z, mod, mode, block, inter) in enumerate(INTERLEAVER_CASES):
+        hd, _ = load_code(code)
+        d, i = po.ref_permutation(hd, Z, mod, mode, block, inter)
+        out["direct_%d" % k], out["inverse_%d" % k] = d, i
+    np.savez_compressed(os.path.join(HERE, "interleaver.npz"), **out)
+    print("interleaver.npz written")
+
+
 def jsonx_name(name, sel):
     return name.replace(".jsonx", "") + ("__" + sel.replace("/", "_") if sel else "") + ".jsonx"
 
@@ -128,7 +145,7 @@ def sim():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["decoders", "demod", "jsonx", "encoder", "sim"]
+    what = sys.argv[1:] or ["decoders", "demod", "jsonx", "encoder", "sim", "interleaver"]
     po.build(ref=True)
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "refmain"])
     for w in what:
