@@ -167,7 +167,7 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
             if (atoi(g) > 0) fgrid = std::min(fgrid, h->num_sms * atoi(g));
         CU(launch_lms_fast(h->fast, io, std::max(fgrid, 1), h->stream));
     } else if (use_fast && (h->decoder_id == LDPCB200_IMS_DEC || h->decoder_id == LDPCB200_MS_DEC)) {
-        int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
+        int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);
         CU(launch_ms_fast(h->fast, h->dp, io, std::max(fgrid, 1), h->stream));
     } else if (use_fast && (h->decoder_id == LDPCB200_TASP_DEC || h->decoder_id == LDPCB200_ASP_DEC || h->decoder_id == LDPCB200_LCHE_DEC || h->decoder_id == LDPCB200_IASP_DEC)) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);

@@ -23,11 +23,14 @@ size_t ms_spec_smem_bytes(int c, int Z)
 }
 
 size_t ms_tmem_smem_bytes(int c, int Z, bool is_int);
+size_t ims_h2_smem_bytes(int c, int Z);
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
-// *variant = 0: check state register-compressed (ms_spec.cuh); 2: messages in tensor memory (ms_tmem.cuh)
+// *variant = 0: check state register-compressed (ms_spec.cuh); 2: messages in tensor memory (ms_tmem.cuh); 4: IMS_DEC with
+// two frames per CTA as fp16 pairs, messages in tensor memory (ims_h2.cuh; the caller asks for it with *variant = 4)
 bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant, bool allow_tmem)
 {
+    const bool want_h2 = *variant == 4 && kind == 2;
     if (g.E > 512 || g.Z > 1024) return false;
     for (int i = 0; i < g.c; i++)
         if (g.cp[i + 1] == g.cp[i]) return false;          // pass A initialises a bit's accumulator through its first edge
@@ -37,7 +40,7 @@ bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_b
         const int hw = *zp / 32;
         int tcols = 32;
         while (tcols < g.E * ((hw + 3) / 4)) tcols *= 2;
-        const size_t need = ms_tmem_smem_bytes(g.c, g.Z, kind == 2);
+        const size_t need = want_h2 ? ims_h2_smem_bytes(g.c, g.Z) : ms_tmem_smem_bytes(g.c, g.Z, kind == 2);
         if (tcols <= 512 && need <= (size_t)smem_per_block) {
             int m = 512 / tcols;
             m = std::min(m, (int)((size_t)smem_per_sm / (need + 1024)));
@@ -46,7 +49,7 @@ bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_b
             if (m >= 1 && m * hw >= 12) {
                 *minb = m;
                 *smem = std::min(lms_tmem_pad_smem(need, m), (size_t)smem_per_block);
-                *variant = 2;
+                *variant = want_h2 ? 4 : 2;
                 return true;
             }
         }
@@ -79,33 +82,46 @@ FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm,
     }
     const char* no_aot = getenv("LDPCB200_NO_AOT");         // 1 (development): compile at run time even when an ahead-of-time instance exists
     const bool use_aot = !(no_aot && *no_aot == '1' && allow_jit);
-    int aot = (tmem && use_aot) ? find_lms_spec_aot(g, kind + 3) : -1;   // 4 / 5: messages in tensor memory (ms_tmem.cuh)
-    if (aot >= 0) p.tmem = 1;
-    else if (use_aot) aot = find_lms_spec_aot(g, kind);
-    if (aot >= 0) {
+    // IMS_DEC as fp16 pairs, two frames per CTA (ims_h2.cuh): exact while every quantity is an integer below 2048 and the
+    // scaling constant of its header exists -- dbits <= 8, 0 <= ialpha <= 16; LDPCB200_IMS_H2=0 keeps one frame per CTA
+    bool h2 = false;
+    if (kind == 2 && tmem) {
+        const int ialpha = (int)(dp.alpha * 16);
+        const char* e = getenv("LDPCB200_IMS_H2");
+        h2 = dp.dbits <= 8 && dp.qbits <= dp.dbits && ialpha >= 0 && ialpha <= 16 && !(e && *e == '0');
+    }
+    // order: ahead-of-time fp16-pair instance; run-time compiled fp16-pair instance; then the one-frame-per-CTA kernels
+    // (tensor memory ahead of time, register-compressed ahead of time, run-time compiled)
+    auto take_aot = [&](int idx, int tm, int fpc) {
         int minb = 1;
-        lms_spec_aot_info(aot, nullptr, &p.threads, &minb, &p.smem_bytes);
-        if (p.smem_bytes <= (size_t)smem_per_block) {
-            p.ok = 1; p.variant = 1; p.ctas_per_sm = minb; p.spec_index = aot; p.jit_kernel = lms_spec_aot_kernel(aot);
-            return p;
-        }
-    }
-    p.tmem = 0;
-    if (allow_jit) {
-        int zp, minb, variant;
+        lms_spec_aot_info(idx, nullptr, &p.threads, &minb, &p.smem_bytes);
+        if (p.smem_bytes > (size_t)smem_per_block) return false;
+        p.ok = 1; p.variant = 1; p.ctas_per_sm = minb; p.spec_index = idx; p.jit_kernel = lms_spec_aot_kernel(idx);
+        p.tmem = tm; p.frames_per_cta = fpc;
+        return true;
+    };
+    auto take_jit = [&](int want_variant, bool allow_tm) {
+        int zp, minb, variant = want_variant;
         size_t smem;
-        if (ms_spec_geometry(g, kind, smem_per_sm, smem_per_block, &zp, &minb, &smem, &variant, tmem)) {
-            std::string why;
-            const void* k = lms_spec_jit(g, zp, minb, variant, kind, why);
-            if (k) {
-                p.ok = 1; p.variant = 2; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem; p.jit_kernel = k;
-                p.tmem = variant == 2;
-                return p;
-            }
-            p.note = why;
-        } else
+        if (!ms_spec_geometry(g, kind, smem_per_sm, smem_per_block, &zp, &minb, &smem, &variant, allow_tm)) {
             p.note = "code does not suit the code-specialised kernel";
-    }
+            return false;
+        }
+        if (want_variant == 4 && variant != 4) return false;
+        std::string why;
+        const void* k = lms_spec_jit(g, zp, minb, variant, kind, why);
+        if (!k) { p.note = why; return false; }
+        p.ok = 1; p.variant = 2; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem; p.jit_kernel = k;
+        p.tmem = variant == 2 || variant == 4;
+        p.frames_per_cta = variant == 4 ? 2 : 1;
+        return true;
+    };
+    int aot;
+    if (h2 && use_aot && (aot = find_lms_spec_aot(g, 7)) >= 0 && take_aot(aot, 1, 2)) return p;
+    if (h2 && allow_jit && take_jit(4, true)) return p;
+    if (tmem && use_aot && (aot = find_lms_spec_aot(g, kind + 3)) >= 0 && take_aot(aot, 1, 1)) return p;   // 4 / 5: messages in tensor memory (ms_tmem.cuh)
+    if (use_aot && (aot = find_lms_spec_aot(g, kind)) >= 0 && take_aot(aot, 0, 1)) return p;
+    if (allow_jit && take_jit(0, tmem)) return p;
     return p;
 }
 

@@ -1,0 +1,397 @@
+// IMS_DEC (imin_sum_decod_qc_lm, decoders.cpp:5430-5690, fixed point, bit-exact) with TWO frames per CTA packed into the
+// two fp16 halves of every 32-bit word: the low half of a register, a shared-memory word or a tensor-memory word belongs to
+// frame 2p, the high half to frame 2p + 1, and every arithmetic instruction (HADD2 / HFMA2 / HMNMX2, sign-bit LOP3) works
+// on both frames at once.  Schedule, summation order and storage are those of ms_tmem.cuh (pass A: acc += message block row
+// by block row; pass B: soft = sat(iy + acc); pass C per check row: v2c, syndrome, new messages as minima over the OTHER
+// edges; messages in TENSOR MEMORY, accumulators / posteriors as doubled columns in the rotation of their last writer).
+//
+// Why this is exact: every IMS_DEC quantity is a small integer -- |iy| <= max_quant, |soft|, |acc| <= max_data = 2^(dbits-1) - 1,
+// |v2c| <= 2 max_data, messages <= max_data -- and binary16 represents every integer up to 2048 and adds, subtracts and
+// compares them exactly; the host only selects this kernel for dbits <= 8 and 0 <= ialpha <= 16.  The one rounding step of
+// the reference, (min * ialpha) >> 4 (:5554, :5640), is floor(m * a / 16):
+//     t = fma(m + d, a / 16, 1025)      d = -k / 16 with 112 / a < k < 128 / a  (a = 12: d = -0.625)
+// m + d is exact (m < 128: the half grid there is 1/16), the fma's exact value is 1025 + q + (r / 16 + d a / 16) with
+// m a = 16 q + r and d a / 16 strictly between -1/2 and -7/16, so the bracket lies strictly inside (-1/2, 1/2) and rounding to
+// the integer grid of [1024, 2048) gives 1025 + q -- never a tie; a second fma with the row's sign (+-1) takes the constant
+// off: +-(t - 1025) = +-q.  (1025, not 1024: with q = 0 the sum stays above 1024, where the grid is 1.)
+// tests/test_message_forms.py checks the identity for every (m, a); tests/test_gpu_ms_spec.py checks ims_y, ims_soft, decisions
+// and iteration counts against the oracle and the register-compressed kernel.
+//
+// A frame that meets the reference's stop rule (:5680-5685) is written out at that moment (its decisions and posteriors are the
+// ones of that iteration); its half of the words keeps being computed -- bounded by the same saturations -- until the partner
+// stops too, and is ignored.  An odd last frame is decoded twice (both halves) and written once.
+// This header must stay free of #include (NVRTC), and follows ms_tmem.cuh in the translation unit.
+#pragma once
+
+namespace ldpcb200 {
+
+// packed binary16 arithmetic on 32-bit registers (PTX, so that NVRTC needs no cuda_fp16.h)
+static __device__ __forceinline__ unsigned h2_add(unsigned a, unsigned b) { unsigned d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+static __device__ __forceinline__ unsigned h2_sub(unsigned a, unsigned b) { unsigned d; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+static __device__ __forceinline__ unsigned h2_mul(unsigned a, unsigned b) { unsigned d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+static __device__ __forceinline__ unsigned h2_fma(unsigned a, unsigned b, unsigned c) { unsigned d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+static __device__ __forceinline__ unsigned h2_fma_relu(unsigned a, unsigned b, unsigned c) { unsigned d; asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+static __device__ __forceinline__ unsigned h2_min(unsigned a, unsigned b) { unsigned d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+static __device__ __forceinline__ unsigned h2_max(unsigned a, unsigned b) { unsigned d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+static __device__ __forceinline__ unsigned h2_abs(unsigned a) { unsigned d; asm("abs.f16x2 %0, %1;" : "=r"(d) : "r"(a)); return d; }
+// {hi, lo} as binary16 (both values are integers below 2048 here: exact)
+static __device__ __forceinline__ unsigned h2_pack(float lo, float hi) { unsigned d; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d; }
+static __device__ __forceinline__ float h2_get(unsigned w, int half)
+{
+    unsigned short h = (unsigned short)(half ? w >> 16 : w & 0xffffu);
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+    return f;
+}
+
+template <class K>
+struct ImsH2 {
+    typedef LmsTmem<K> T;
+    static constexpr int B = K::B, C = K::C, Z = K::Z, N = K::C * K::Z, R = K::B * K::Z, ZP = K::ZP, E = K::E;
+    static constexpr int NWORDS = (N + 31) / 32;
+    static constexpr bool ALL_ACTIVE = (Z == ZP);
+    static constexpr int CS = 2 * Z;
+    static constexpr int NWARPS = ZP / 32;
+    static constexpr int TCOLS = K::TCOLS;
+    // shared memory (words; one word = the two frames' halves): doubled accumulators / posteriors (also the staging of
+    // the two frames' fp32 LLRs before the quantiser: 2 N words) | quantised channel values | mbarrier | misc
+    static constexpr int Y_OFF = C * CS;
+    static constexpr int MBAR_OFF = (Y_OFF + N + 1) & ~1;
+    static constexpr int MISC_OFF = MBAR_OFF + 2;
+    static constexpr int SMEM_WORDS = MISC_OFF + 8;
+
+    struct Consts { unsigned cap, ncap, cap2, scale, dshift, magic, sone; };
+
+    // ---- pass A, block row J: acc[bit] = sat(acc[bit] + message), ascending block rows per bit (:5540-5576).  The
+    // accumulators are kept BIASED by max_data (0 .. 2 max_data), so that the saturation is one fma with a built-in
+    // max(., 0) and one minimum instead of an add and two comparisons; pass B takes the bias off (y holds iy - max_data).
+    template <int J, int Q>
+    static __device__ __forceinline__ void accA_load(const unsigned* softn, unsigned (&acc)[K::RP[J + 1] - K::RP[J]], unsigned cap)
+    {
+        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q < DEG) {
+            constexpr int off = K::COL[E0 + Q] * CS + K::DELTA[E0 + Q];
+            if constexpr (K::FIRST[E0 + Q]) acc[Q] = cap;                                        // 0 + bias, :5536
+            else acc[Q] = softn[off];
+            accA_load<J, Q + 1>(softn, acc, cap);
+        }
+    }
+    template <int J, int Q>
+    static __device__ __forceinline__ void accA_store(unsigned* softn, bool active, const unsigned (&acc)[K::RP[J + 1] - K::RP[J]])
+    {
+        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q < DEG) {
+            constexpr int off = K::COL[E0 + Q] * CS;
+            if (ALL_ACTIVE || active) { softn[off] = acc[Q]; softn[off + Z] = acc[Q]; }
+            accA_store<J, Q + 1>(softn, active, acc);
+        }
+    }
+    template <int J>
+    static __device__ __forceinline__ void passA(unsigned* softn, unsigned trow, unsigned mbar, unsigned& ph, bool lane0, bool active, const Consts& k)
+    {
+        if constexpr (J < B) {
+            constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+            unsigned msg[DEG], acc[DEG];
+            tmem_ld_n<DEG>(trow + E0, msg);
+            accA_load<J, 0>(softn, acc, k.cap);
+            tmem_wait_ld<DEG>(msg);
+#pragma unroll
+            for (int q = 0; q < DEG; q++) acc[q] = h2_min(h2_fma_relu(acc[q], k.sone, msg[q]), k.cap2);       // :5567-5568
+            T::loads_done(mbar, lane0);
+            if constexpr (B % 2 == 0) T::wait_loads(mbar, J & 1);
+            else { T::wait_loads(mbar, ph); ph ^= 1u; }
+            accA_store<J, 0>(softn, active, acc);
+            __syncthreads();
+            passA<J + 1>(softn, trow, mbar, ph, lane0, active, k);
+        }
+    }
+
+    // ---- pass B, position tid of every column: soft = sat(iy + acc) (:5594-5603) = sat((iy - max_data) + biased acc); the column
+    // is rotated by K::ROT, the channel values are not
+    template <int COL>
+    static __device__ __forceinline__ void passB(unsigned* softn, const unsigned* y, int tid, const Consts& k)
+    {
+        if constexpr (COL < C) {
+            constexpr int rot = K::ROT[COL];
+            int p = tid + rot;
+            if (rot != 0 && p >= Z) p -= Z;
+            const unsigned s = h2_max(h2_min(h2_add(y[COL * Z + p], softn[COL * CS]), k.cap), k.ncap);
+            softn[COL * CS] = s; softn[COL * CS + Z] = s;
+            passB<COL + 1>(softn, y, tid, k);
+        }
+    }
+
+    // ---- pass C, block row J (:5608-5678)
+    template <int J, int Q>
+    static __device__ __forceinline__ void softC_load(const unsigned* softn, unsigned (&rs)[K::RP[J + 1] - K::RP[J]])
+    {
+        constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+        if constexpr (Q < DEG) {
+            constexpr int off = K::COL[E0 + Q] * CS + K::SYNSH[E0 + Q];
+            rs[Q] = softn[off];
+            softC_load<J, Q + 1>(softn, rs);
+        }
+    }
+    // m[q] = min(cap, min over p != q of |v[p]|): prefix / suffix minima, 3 DEG - 4 two-input minima for both frames
+    template <int DEG>
+    static __device__ __forceinline__ void min_of_others(const unsigned (&v)[DEG], unsigned (&m)[DEG], unsigned cap)
+    {
+        if constexpr (DEG == 1) m[0] = cap;
+        else {
+            unsigned pre[DEG], suf[DEG];                         // pre[i] = min(cap, |v[0..i]|), suf[i] = min(cap, |v[i..]|)
+            pre[0] = h2_min(h2_abs(v[0]), cap);
+            suf[DEG - 1] = h2_min(h2_abs(v[DEG - 1]), cap);
+#pragma unroll
+            for (int i = 1; i < DEG - 1; i++) pre[i] = h2_min(pre[i - 1], h2_abs(v[i]));
+#pragma unroll
+            for (int i = DEG - 2; i > 0; i--) suf[i] = h2_min(suf[i + 1], h2_abs(v[i]));
+            m[0] = suf[1];
+            m[DEG - 1] = pre[DEG - 2];
+#pragma unroll
+            for (int i = 1; i < DEG - 1; i++) m[i] = h2_min(pre[i - 1], suf[i + 1]);
+        }
+    }
+    template <int J>
+    static __device__ __forceinline__ void passC(const unsigned* softn, unsigned trow, const Consts& k, unsigned& bad)
+    {
+        if constexpr (J < B) {
+            constexpr int E0 = K::RP[J], DEG = K::RP[J + 1] - K::RP[J];
+            unsigned msg[DEG], rs[DEG], v[DEG], m[DEG];
+            tmem_ld_n<DEG>(trow + E0, msg);
+            softC_load<J, 0>(softn, rs);
+            tmem_wait_ld<DEG>(msg);
+            unsigned synd = 0, sacc = 0;
+#pragma unroll
+            for (int q = 0; q < DEG; q++) {
+                synd ^= rs[q];                                                                   // :5631 (sign bits = rs < 0, both frames)
+                v[q] = h2_sub(rs[q], msg[q]);                                                    // :5646, the message is already scaled (:5640)
+                sacc ^= v[q];
+            }
+            // the row's sign product as +-1 per frame, and -+1025 to take the rounding constant off again
+            const unsigned rone = (sacc & 0x80008000u) | k.sone;
+            const unsigned nmag = h2_mul(rone, k.magic ^ 0x80008000u);
+            min_of_others<DEG>(v, m, k.cap);                                                     // :5653, :5656-5666
+#pragma unroll
+            for (int q = 0; q < DEG; q++) {
+                const unsigned t = h2_fma(h2_add(m[q], k.dshift), k.scale, k.magic);             // 1025 + ((m * ialpha) >> 4), :5554
+                msg[q] = h2_fma(t, rone, nmag) ^ (v[q] & 0x80008000u);                            // row sign, then the edge's own sign
+            }
+            bad |= synd;
+            tmem_st_n<DEG>(trow + E0, msg);                                                      // :5675
+            passC<J + 1>(softn, trow, k, bad);
+        }
+    }
+
+    // channel LLRs of frame f as fp32 into dst[N] (the first load of ms_tmem.cuh)
+    static __device__ __forceinline__ void load_frame(const FrameIO& io, int f, float* dst, int tid)
+    {
+        if (io.ch.enabled) {
+            const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
+            if (io.ch.m > 2) {
+                const int half = io.ch.m >> 1, ncomp = 2 * (N / io.ch.m);
+                for (int c = tid; c < ncomp; c += ZP) {
+                    float o[4];
+                    channel_llr_qam_component(io.ch, frame, c, o);
+                    const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
+                    for (int b = 0; b < half; b++) {
+                        const int i = channel_dest(io.ch, i0 + b);
+                        dst[i] = i >= io.ch.punct_start ? io.ch.punct_value : o[b];
+                    }
+                }
+            } else {
+                for (int i4 = tid; i4 < N / 4; i4 += ZP) {                                // one Philox block -> four LLRs
+                    float o[4];
+                    int d[4];
+                    channel_llr4_bpsk(io.ch, frame, i4, o, d);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) dst[d[b]] = o[b];
+                }
+                for (int j = (N & ~3) + tid; j < N; j += ZP) { const int i = channel_dest(io.ch, j); dst[i] = channel_llr(io.ch, frame, i); }
+            }
+        } else if (io.llr_dtype == 1) {
+            const float* src = (const float*)io.llr + (size_t)f * N;
+            for (int i = tid; i < N; i += ZP) dst[i] = __ldcs(src + i);
+        } else {
+            const double* src = (const double*)io.llr + (size_t)f * N;
+            for (int i = tid; i < N; i += ZP) dst[i] = (float)__ldcs(src + i);
+        }
+    }
+    // the quantiser of :5481-5500 for one value
+    static __device__ __forceinline__ int quantise(double val, double coef, const MsSpecParams& sp)
+    {
+        int sign = 0;
+        if (val < 0) { val = -val; sign = 1; }
+        val *= coef;
+        if (val > sp.thr) val = sp.thr;
+        const int ival = (short)floor(div_normal(val * sp.max_quant, sp.thr) + 0.5);   // the correctly rounded quotient without the slow-path branch (channel.cuh)
+        return sign ? -ival : ival;
+    }
+
+    // outputs of frame f = half `h` of the posteriors (the whole CTA calls this)
+    static __device__ __forceinline__ void emit(const FrameIO& io, const unsigned* soft2, int* s_misc, int f, int h, int ret, int tid, bool active)
+    {
+        if (io.post) {
+            for (int col = 0; col < C; col++)
+                if (ALL_ACTIVE || active)
+                    ((short*)io.post)[(size_t)f * N + col * Z + tid] = (short)(int)h2_get(soft2[col * CS + tid + K::rt_ri()[col]], h);
+        }
+        const int lane = tid & 31;
+        const unsigned sbit = h ? 0x80000000u : 0x8000u;
+        int nerr = 0, nerr_info = 0;
+        constexpr int NROUND = (N + 31) & ~31;
+        if (tid == 0) { s_misc[1] = 0; s_misc[2] = 0; }
+        __syncthreads();
+        for (int i = tid; i < NROUND; i += ZP) {
+            int bit = 0;
+            if (i < N) {
+                const int col = i / Z, p = i - col * Z;
+                bit = (soft2[col * CS + p + K::rt_ri()[col]] & sbit) != 0u;
+            }
+            const unsigned w = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) {
+                if (io.hard_words) io.hard_words[(size_t)f * NWORDS + (i >> 5)] = w;
+                nerr += __popc(w);
+                const int lo = R - i;
+                const unsigned wi = lo <= 0 ? w : (lo >= 32 ? 0u : (w >> lo) << lo);
+                nerr_info += __popc(wi);
+            }
+        }
+        if (lane == 0 && nerr) { atomicAdd(&s_misc[1], nerr); atomicAdd(&s_misc[2], nerr_info); }
+        __syncthreads();
+        if (tid == 0) {
+            const int e = s_misc[1], ei = s_misc[2];
+            if (io.iters) io.iters[f] = ret;
+            if (io.per_frame)
+                io.per_frame[f] = (e ? 0x80000000u : 0u) | (ret >= 0 ? 0x40000000u : 0u) | (unsigned)(ei < 0xFFFFFF ? ei : 0xFFFFFF);
+            if (io.counters) {
+                atomicAdd(&io.counters[0], 1ull);
+                atomicAdd(&io.counters[4], (unsigned long long)(ret < 0 ? -ret : ret));
+                if (e) {
+                    atomicAdd(&io.counters[1], 1ull);
+                    atomicAdd(&io.counters[2], (unsigned long long)ei);
+                    atomicAdd(&io.counters[5], (unsigned long long)e);
+                    if (ret >= 0) atomicAdd(&io.counters[3], 1ull);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    static __device__ __forceinline__ void kernel(const FrameIO& io, const MsSpecParams& sp)
+    {
+        extern __shared__ __align__(16) unsigned soft2u[];
+        unsigned* soft2 = soft2u;
+        unsigned* y = soft2 + Y_OFF;                             // quantised channel values, bit order, {frame 2p+1, frame 2p}
+        int* s_misc = (int*)(soft2 + MISC_OFF);
+        const int tid = threadIdx.x;
+        const bool active = tid < Z;
+        const bool lane0 = (tid & 31) == 0;
+        const bool noexit = io.flags & 8u;                       // LDPCB200_NO_EARLY_EXIT
+        unsigned* softn = soft2 + tid;
+        const unsigned mbar = (unsigned)__cvta_generic_to_shared(soft2 + MBAR_OFF);
+        unsigned ph = 0;
+
+        Consts k;
+        {
+            const float cap = (float)sp.max_data;
+            k.cap = h2_pack(cap, cap);
+            k.ncap = k.cap ^ 0x80008000u;
+            k.cap2 = h2_pack(2.0f * cap, 2.0f * cap);
+            const float sc = (float)sp.ialpha * 0.0625f;
+            k.scale = h2_pack(sc, sc);
+            // d = -kk / 16, 112 / a < kk < 128 / a (none needed for a = 0 and a = 16: the product is an integer)
+            const int a = sp.ialpha;
+            const int kk = (a <= 0 || a >= 16) ? 0 : 112 / a + 1;
+            const float d = -(float)kk * 0.0625f;
+            k.dshift = h2_pack(d, d);
+            k.magic = h2_pack(1025.0f, 1025.0f);
+            k.sone = h2_pack(1.0f, 1.0f);
+        }
+
+        if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"((unsigned)NWARPS) : "memory");
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"((unsigned)__cvta_generic_to_shared(s_misc)), "r"((unsigned)TCOLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned tbase = *(volatile unsigned*)s_misc;
+        const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * E), 0);
+        const int npairs = (io.nf + 1) >> 1;
+
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_misc[0] = (int)atomicAdd(io.next_frame, 1u);
+            __syncthreads();
+            const int pair = s_misc[0];
+            if (pair >= npairs) break;
+            const int fa = 2 * pair, fb = 2 * pair + 1 < io.nf ? 2 * pair + 1 : fa;       // an odd last frame rides in both halves
+            const bool twins = fb == fa;
+
+            // ---- first load: the two frames' fp32 LLRs into the (still unused) posterior area, then the quantiser
+            float* stage = (float*)soft2;
+            load_frame(io, fa, stage, tid);
+            if (!twins) load_frame(io, fb, stage + N, tid);
+            tmem_zero_n<E>(trow);                                                    // dcs[] = 0, :5463-5502
+            tmem_wait_st();
+            __syncthreads();
+            {
+                // per-frame energy normalisation (:5472-5479): coef comes from the energy pre-pass (channel.cu ims_energy_kernel)
+                const bool f64 = !io.ch.enabled && io.llr_dtype == 0;               // doubles are quantised as doubles, not through fp32
+                const double* sa = f64 ? (const double*)io.llr + (size_t)fa * N : nullptr;
+                const double* sb = f64 ? (const double*)io.llr + (size_t)fb * N : nullptr;
+                const double ca = io.coef[fa], cb = io.coef[fb];
+                for (int i = tid; i < N; i += ZP) {
+                    const int qa = quantise(sa ? sa[i] : (double)stage[i], ca, sp);
+                    const int qb = twins ? qa : quantise(sb ? sb[i] : (double)stage[N + i], cb, sp);
+                    y[i] = h2_pack((float)(qa - sp.max_data), (float)(qb - sp.max_data));       // iy - max_data: pass B
+                    if (io.aux) {
+                        io.aux[(size_t)fa * N + i] = (short)qa;
+                        if (!twins) io.aux[(size_t)fb * N + i] = (short)qb;
+                    }
+                }
+                __syncthreads();
+            }
+
+            int reta = 0, retb = 0, pa = 1, pb = 1, iter;
+            bool seta = false, setb = false, donea = false, doneb = twins;
+            for (iter = 0; iter < io.maxiter; iter++) {
+                tmem_wait_st();
+                passA<0>(softn, trow, mbar, ph, lane0, active, k);                               // STATE 1
+                if (ALL_ACTIVE || active) passB<0>(softn, y, tid, k);                            // STATE 2
+                __syncthreads();
+                unsigned bad = 0;                                                                // STATE 3
+                passC<0>(softn, trow, k, bad);
+                if (!(ALL_ACTIVE || active)) bad = 0;
+                pa = __syncthreads_or((int)((bad >> 15) & 1u));
+                pb = __syncthreads_or((int)(bad >> 31));
+                if (!pa && !seta) { reta = iter + 1; seta = true; if (!noexit) { emit(io, soft2, s_misc, fa, 0, reta, tid, active); donea = true; } }
+                if (!pb && !setb) { retb = iter + 1; setb = true; if (!noexit && !twins) { emit(io, soft2, s_misc, fb, 1, retb, tid, active); doneb = true; } }
+                if (!noexit && donea && doneb) break;                                            // :5680-5685
+            }
+            if (io.maxiter <= 0) {                                                               // no pass ran: decisions of the channel values
+                for (int col = 0; col < C; col++)
+                    if (ALL_ACTIVE || active) {
+                        int p = tid + K::rt_rot()[col];
+                        if (p >= Z) p -= Z;
+                        const unsigned w = h2_add(y[col * Z + p], k.cap);
+                        softn[col * CS] = w; softn[col * CS + Z] = w;
+                    }
+                __syncthreads();
+            }
+            if (!donea) emit(io, soft2, s_misc, fa, 0, seta ? reta : (pa ? -iter : iter + 1), tid, active);   // :5689
+            if (!doneb) emit(io, soft2, s_misc, fb, 1, setb ? retb : (pb ? -iter : iter + 1), tid, active);
+        }
+
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)TCOLS) : "memory");
+        }
+    }
+};
+
+} // namespace ldpcb200

@@ -85,3 +85,50 @@ def test_ms_ims_simulate_consistency(ldpc, po):
         errs = out["hard"].sum(axis=1)
         assert sim["frame_errors"] == int((errs > 0).sum()) and sim["bit_errors"] == int(errs.sum())
         assert sim["iter_sum"] == int(np.abs(out["iters"]).sum())
+
+
+@pytest.mark.parametrize("code,Z,snr", [("ref32x16_a", 126, 3.0), ("c4_wifi_12x24", 81, 2.5), ("ref32x16_b", 256, 2.0)])
+def test_ims_fp16_pairs_two_frames_per_cta(ldpc, po, monkeypatch, code, Z, snr):
+    """ims_h2.cuh: two frames per CTA as fp16 pairs.  Odd batches (the last frame rides alone), a single frame, frames of a pair
+    that stop at different iterations, fixed iterations, zero iterations -- all bit-exact against the oracle, and equal to the
+    one-frame-per-CTA kernel (LDPCB200_IMS_H2=0)."""
+    hd, llr = _case(code, Z, snr, 151, seed=33)
+    want = po.orc_decode(po.IMS, hd, Z, llr, 15)
+    assert len(set(want["iters"].tolist())) > 3                          # partners stop at different iterations
+    with ldpc.Decoder(hd, Z, po.IMS, use_fast=2) as d:
+        info = d.kernel_info()
+        assert info["frames_per_cta"] == 2 and info["tmem"], info
+        got = d.decode(llr, 15, want_post=True, want_aux=True)
+        one = d.decode(llr[17:18], 15, want_post=True)
+        nx = d.decode(llr, 15, no_early_exit=True)
+        z = d.decode(llr[:5], 0, want_post=True)
+        sim = d.simulate(snr, 101, 15, seed=8, want_per_frame=True)
+        again = d.decode(d.generate_llr(snr, 101, seed=8), 15)
+    for key in ("aux", "iters", "hard", "post"):
+        assert np.array_equal(got[key], want[key]), key
+    assert np.array_equal(one["iters"], want["iters"][17:18]) and np.array_equal(one["post"], want["post"][17:18])
+    assert np.array_equal(nx["iters"], want["iters"])
+    assert np.array_equal(z["iters"], np.zeros(5, np.int32))              # no pass ran: decisions of the QUANTISED channel values
+    assert np.array_equal(z["hard"], (want["aux"][:5] < 0).astype(np.uint8)) and np.array_equal(z["post"], want["aux"][:5])
+    errs = again["hard"].sum(axis=1)
+    assert np.array_equal(sim["per_frame"] >> 31, (errs > 0).astype(np.uint32))
+    assert sim["iter_sum"] == int(np.abs(again["iters"]).sum()) and sim["frames"] == 101
+    monkeypatch.setenv("LDPCB200_IMS_H2", "0")
+    with ldpc.Decoder(hd, Z, po.IMS, use_fast=2) as d:
+        assert d.kernel_info()["frames_per_cta"] == 1
+        ref = d.decode(llr, 15, want_post=True)
+        nx1 = d.decode(llr, 15, no_early_exit=True, want_post=True)
+    assert np.array_equal(ref["post"], got["post"]) and np.array_equal(ref["iters"], got["iters"])
+    with ldpc.Decoder(hd, Z, po.IMS, use_fast=2, dbits=9) as d:           # dbits = 9: integers up to 255 * 12 -- not this kernel
+        assert d.kernel_info()["frames_per_cta"] == 1
+
+
+def test_ims_fp16_pairs_other_alpha(ldpc, po):
+    """Every scaling constant ialpha = 0 .. 16 of the fp16-pair kernel against the oracle (run-time compiled instance)."""
+    hd, llr = _case("c4_wifi_12x24", 81, 2.5, 40, seed=2)
+    for alpha in (0.0, 0.07, 0.3, 0.5, 0.8125, 0.95, 1.0):
+        want = po.orc_decode(po.IMS, hd, 81, llr, 10, alpha=alpha)
+        with ldpc.Decoder(hd, 81, po.IMS, use_fast=2, alpha=alpha) as d:
+            assert d.kernel_info()["frames_per_cta"] == 2
+            got = d.decode(llr, 10, want_post=True)
+        assert np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["post"], want["post"]), alpha

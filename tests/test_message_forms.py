@@ -121,3 +121,27 @@ def test_grouped_minima_cover_every_other_edge_exactly_once():
         for cap in (f32(32767.0), CAP, f32(127.0)):
             want = np.stack([np.minimum(np.min(np.delete(a, q, axis=1), axis=1, initial=np.inf), cap) for q in range(deg)], axis=1).astype(f32)
             assert np.array_equal(grouped_min_of_others(a, cap), want), (deg, cap)
+
+
+def test_ims_shift_as_two_binary16_fmas():
+    """csrc/ims_h2.cuh: floor(m * a / 16) = fma(m + d, a / 16, 1025) - 1025 in binary16 round-to-nearest, d = -k / 16 with
+    112 / a < k < 128 / a (none for a = 0, 16), for every m <= 127 and every ialpha 0 .. 16; the sign step
+    fma(t, +-1, -+1025) then gives +-floor exactly (decoders.cpp:5554, :5640)."""
+    f16 = np.float16
+    m = np.arange(0, 128, dtype=np.float64)
+    for a in range(0, 17):
+        k = 0 if a in (0, 16) else 112 // a + 1
+        if k:
+            assert 112 / a < k < 128 / a
+        d = -k / 16.0
+        md = (m + d).astype(f16)
+        assert np.array_equal(md.astype(np.float64), m + d)                    # m + d is exact on the half grid
+        t = (md.astype(np.float64) * (a / 16.0) + 1025.0).astype(f16)          # one rounding: the fma
+        want = np.floor(m * a / 16.0)
+        assert np.array_equal(t.astype(np.float64) - 1025.0, want), a
+        for s in (1.0, -1.0):
+            q = (t.astype(np.float64) * s - 1025.0 * s).astype(f16)
+            assert np.array_equal(q.astype(np.float64), s * want)
+    # every quantity of IMS_DEC with dbits <= 8 is an integer binary16 holds exactly
+    ints = np.arange(-2048, 2049)
+    assert np.array_equal(ints.astype(f16).astype(np.int64), ints)
