@@ -167,7 +167,7 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
             if (atoi(g) > 0) fgrid = std::min(fgrid, h->num_sms * atoi(g));
         CU(launch_lms_fast(h->fast, io, std::max(fgrid, 1), h->stream));
     } else if (use_fast && (h->decoder_id == LDPCB200_IMS_DEC || h->decoder_id == LDPCB200_MS_DEC)) {
-        int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);
+        int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);   // ims_h2: frames in flight per CTA
         CU(launch_ms_fast(h->fast, h->dp, io, std::max(fgrid, 1), h->stream));
     } else if (use_fast && (h->decoder_id == LDPCB200_TASP_DEC || h->decoder_id == LDPCB200_ASP_DEC || h->decoder_id == LDPCB200_LCHE_DEC || h->decoder_id == LDPCB200_IASP_DEC)) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
@@ -642,7 +642,10 @@ int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int
     if (!lms_spec_geometry(g, 233472, 232448, &zp, &minb, &smem, &variant, !(no_tmem && *no_tmem == '1'))) return fail(LDPCB200_EUNSUPPORTED, "code does not suit the code-specialised kernel");
     std::vector<char> cubin;
     std::string why;
-    if (!lms_spec_compile(lms_spec_generate(g, zp, minb, variant, 0), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());
+    int kind = 0;
+    if (const char* e = getenv("LDPCB200_JIT_CHECK"))           // development: "kind,variant,minb" of another kernel family (spec_jit.cpp)
+        sscanf(e, "%d,%d,%d", &kind, &variant, &minb);
+    if (!lms_spec_compile(lms_spec_generate(g, zp, minb, variant, kind), sm_major, sm_minor, cubin, why)) return fail(LDPCB200_EUNSUPPORTED, "%s", why.c_str());
     if (cubin_bytes) *cubin_bytes = (int)cubin.size();
     return 0;
 }

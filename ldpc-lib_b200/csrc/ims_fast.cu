@@ -23,11 +23,23 @@ size_t ms_spec_smem_bytes(int c, int Z)
 }
 
 size_t ms_tmem_smem_bytes(int c, int Z, bool is_int);
-size_t ims_h2_smem_bytes(int c, int Z);
+size_t ims_h2_smem_bytes(int c, int Z, int groups);
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
-// *variant = 0: check state register-compressed (ms_spec.cuh); 2: messages in tensor memory (ms_tmem.cuh); 4: IMS_DEC with
-// two frames per CTA as fp16 pairs, messages in tensor memory (ims_h2.cuh; the caller asks for it with *variant = 4)
+// groups of (Z rounded up to 32) threads per CTA of the fp16-pair IMS_DEC kernel: two when a group is at most four warps
+// (LDPCB200_IMS_H2_GROUPS=1|2 overrides; development)
+int ims_h2_groups(int Z)
+{
+    const int zp = (Z + 31) & ~31;
+    int g = zp <= 128 ? 2 : 1;
+    if (const char* e = getenv("LDPCB200_IMS_H2_GROUPS"))
+        if (atoi(e) == 1 || (atoi(e) == 2 && 2 * zp <= 1024)) g = atoi(e);
+    return g;
+}
+
+// *variant = 0: check state register-compressed (ms_spec.cuh); 2: messages in tensor memory (ms_tmem.cuh); 4 / 5: IMS_DEC with
+// the frames as fp16 pairs, one / two groups of *zp threads per CTA, messages in tensor memory (ims_h2.cuh; the caller asks
+// for it with *variant = 4).  *zp = threads per group.
 bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_block, int* zp, int* minb, size_t* smem, int* variant, bool allow_tmem)
 {
     const bool want_h2 = *variant == 4 && kind == 2;
@@ -37,23 +49,25 @@ bool ms_spec_geometry(const QcHost& g, int kind, int smem_per_sm, int smem_per_b
     *zp = (g.Z + 31) & ~31;
     *variant = 0;
     if (allow_tmem && g.maxdeg <= 32) {                     // (plan_ms_fast clears allow_tmem when IMS_DEC's integers would not be exact in fp32)
-        const int hw = *zp / 32;
+        const int groups = want_h2 ? ims_h2_groups(g.Z) : 1, nt = groups * *zp;
+        const int hw = nt / 32;
         int tcols = 32;
         while (tcols < g.E * ((hw + 3) / 4)) tcols *= 2;
-        const size_t need = want_h2 ? ims_h2_smem_bytes(g.c, g.Z) : ms_tmem_smem_bytes(g.c, g.Z, kind == 2);
-        if (tcols <= 512 && need <= (size_t)smem_per_block) {
+        const size_t need = want_h2 ? ims_h2_smem_bytes(g.c, g.Z, groups) : ms_tmem_smem_bytes(g.c, g.Z, kind == 2);
+        if (tcols <= 512 && need <= (size_t)smem_per_block && nt <= 1024) {
             int m = 512 / tcols;
             m = std::min(m, (int)((size_t)smem_per_sm / (need + 1024)));
-            m = std::min(m, 2048 / *zp);
-            m = std::min(m, 65536 / (*zp * 64));
-            if (m >= 1 && m * hw >= 12) {
+            m = std::min(m, 2048 / nt);
+            m = std::min(m, 65536 / (nt * (want_h2 ? 128 : 64)));
+            if (m >= 1 && m * hw >= (want_h2 ? 8 : 12)) {
                 *minb = m;
                 *smem = std::min(lms_tmem_pad_smem(need, m), (size_t)smem_per_block);
-                *variant = want_h2 ? 4 : 2;
+                *variant = want_h2 ? 3 + groups : 2;
                 return true;
             }
         }
     }
+    if (want_h2) return false;
     if (g.b > 32 || g.maxdeg > 16) return false;
     *smem = ms_spec_smem_bytes(g.c, g.Z);
     if (*smem > (size_t)smem_per_block) return false;
@@ -107,17 +121,18 @@ FastPlan plan_ms_fast(const QcHost& g, int kind, int precision, int smem_per_sm,
             p.note = "code does not suit the code-specialised kernel";
             return false;
         }
-        if (want_variant == 4 && variant != 4) return false;
+        if (want_variant == 4 && variant < 4) return false;
         std::string why;
         const void* k = lms_spec_jit(g, zp, minb, variant, kind, why);
         if (!k) { p.note = why; return false; }
-        p.ok = 1; p.variant = 2; p.ctas_per_sm = minb; p.threads = zp; p.smem_bytes = smem; p.jit_kernel = k;
-        p.tmem = variant == 2 || variant == 4;
-        p.frames_per_cta = variant == 4 ? 2 : 1;
+        p.ok = 1; p.variant = 2; p.ctas_per_sm = minb; p.threads = variant == 5 ? 2 * zp : zp; p.smem_bytes = smem; p.jit_kernel = k;
+        p.tmem = variant == 2 || variant >= 4;
+        p.frames_per_cta = variant >= 4 ? 2 * (variant - 3) : 1;
         return true;
     };
     int aot;
-    if (h2 && use_aot && (aot = find_lms_spec_aot(g, 7)) >= 0 && take_aot(aot, 1, 2)) return p;
+    const int groups = ims_h2_groups(g.Z);
+    if (h2 && use_aot && (aot = find_lms_spec_aot(g, 6 + groups)) >= 0 && take_aot(aot, 1, 2 * groups)) return p;
     if (h2 && allow_jit && take_jit(4, true)) return p;
     if (tmem && use_aot && (aot = find_lms_spec_aot(g, kind + 3)) >= 0 && take_aot(aot, 1, 1)) return p;   // 4 / 5: messages in tensor memory (ms_tmem.cuh)
     if (use_aot && (aot = find_lms_spec_aot(g, kind)) >= 0 && take_aot(aot, 0, 1)) return p;

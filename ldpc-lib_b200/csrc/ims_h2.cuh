@@ -17,9 +17,14 @@
 // tests/test_message_forms.py checks the identity for every (m, a); tests/test_gpu_ms_spec.py checks ims_y, ims_soft, decisions
 // and iteration counts against the oracle and the register-compressed kernel.
 //
-// A frame that meets the reference's stop rule (:5680-5685) is written out at that moment (its decisions and posteriors are the
-// ones of that iteration); its half of the words keeps being computed -- bounded by the same saturations -- until the partner
-// stops too, and is ignored.  An odd last frame is decoded twice (both halves) and written once.
+// Frames are independent and stop at different iterations (:5680-5685), so the halves are SLOTS: a CTA owns 2 G of them (G
+// groups of ZP threads -- two groups when Z <= 128, so that a CTA has eight warps that walk the unrolled block rows
+// together and share the instruction cache), every iteration runs on all of them, and a slot whose frame stops (syndrome
+// zero, or the iteration limit) is written out at that moment and refilled with the next frame of the batch: its half of
+// the channel words is rewritten, its half of the message words in tensor memory is cleared, its iteration count starts
+// over, while the other slots carry on.  The accumulators / posteriors are rebuilt from the messages in every iteration
+// (pass A starts from 0), so nothing else has to be reset.  A slot without a frame keeps computing on bounded values and
+// is ignored.
 // This header must stay free of #include (NVRTC), and follows ms_tmem.cuh in the translation unit.
 #pragma once
 
@@ -44,21 +49,26 @@ static __device__ __forceinline__ float h2_get(unsigned w, int half)
     return f;
 }
 
-template <class K>
+template <class K, int G>
 struct ImsH2 {
     typedef LmsTmem<K> T;
     static constexpr int B = K::B, C = K::C, Z = K::Z, N = K::C * K::Z, R = K::B * K::Z, ZP = K::ZP, E = K::E;
+    static constexpr int NT = G * ZP;                           // threads per CTA
+    static constexpr int S = 2 * G;                             // slots = frames in flight per CTA
     static constexpr int NWORDS = (N + 31) / 32;
     static constexpr bool ALL_ACTIVE = (Z == ZP);
     static constexpr int CS = 2 * Z;
-    static constexpr int NWARPS = ZP / 32;
-    static constexpr int TCOLS = K::TCOLS;
-    // shared memory (words; one word = the two frames' halves): doubled accumulators / posteriors (also the staging of
-    // the two frames' fp32 LLRs before the quantiser: 2 N words) | quantised channel values | mbarrier | misc
+    static constexpr int NWARPS = NT / 32;
+    static __host__ __device__ constexpr int pow2_at_least(int n) { int t = 32; while (t < n) t *= 2; return t; }
+    static constexpr int TCOLS = pow2_at_least(E * ((NT / 32 + 3) / 4));
+    // shared memory (words; one word = the two slots' halves), per group: doubled accumulators / posteriors (between
+    // iterations also the staging of a new frame's fp32 LLRs: N of its 2 N words) | quantised channel values (minus
+    // max_data, see pass A); then mbarrier | misc
     static constexpr int Y_OFF = C * CS;
-    static constexpr int MBAR_OFF = (Y_OFF + N + 1) & ~1;
+    static constexpr int GROUP_WORDS = (Y_OFF + N + 1) & ~1;
+    static constexpr int MBAR_OFF = G * GROUP_WORDS;
     static constexpr int MISC_OFF = MBAR_OFF + 2;
-    static constexpr int SMEM_WORDS = MISC_OFF + 8;
+    static constexpr int SMEM_WORDS = MISC_OFF + 16;
 
     struct Consts { unsigned cap, ncap, cap2, scale, dshift, magic, sone; };
 
@@ -182,14 +192,14 @@ struct ImsH2 {
         }
     }
 
-    // channel LLRs of frame f as fp32 into dst[N] (the first load of ms_tmem.cuh)
+    // channel LLRs of frame f as fp32 into dst[N] (the first load of ms_tmem.cuh; all NT threads)
     static __device__ __forceinline__ void load_frame(const FrameIO& io, int f, float* dst, int tid)
     {
         if (io.ch.enabled) {
             const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
             if (io.ch.m > 2) {
                 const int half = io.ch.m >> 1, ncomp = 2 * (N / io.ch.m);
-                for (int c = tid; c < ncomp; c += ZP) {
+                for (int c = tid; c < ncomp; c += NT) {
                     float o[4];
                     channel_llr_qam_component(io.ch, frame, c, o);
                     const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
@@ -199,21 +209,21 @@ struct ImsH2 {
                     }
                 }
             } else {
-                for (int i4 = tid; i4 < N / 4; i4 += ZP) {                                // one Philox block -> four LLRs
+                for (int i4 = tid; i4 < N / 4; i4 += NT) {                                // one Philox block -> four LLRs
                     float o[4];
                     int d[4];
                     channel_llr4_bpsk(io.ch, frame, i4, o, d);
 #pragma unroll
                     for (int b = 0; b < 4; b++) dst[d[b]] = o[b];
                 }
-                for (int j = (N & ~3) + tid; j < N; j += ZP) { const int i = channel_dest(io.ch, j); dst[i] = channel_llr(io.ch, frame, i); }
+                for (int j = (N & ~3) + tid; j < N; j += NT) { const int i = channel_dest(io.ch, j); dst[i] = channel_llr(io.ch, frame, i); }
             }
         } else if (io.llr_dtype == 1) {
             const float* src = (const float*)io.llr + (size_t)f * N;
-            for (int i = tid; i < N; i += ZP) dst[i] = __ldcs(src + i);
+            for (int i = tid; i < N; i += NT) dst[i] = __ldcs(src + i);
         } else {
             const double* src = (const double*)io.llr + (size_t)f * N;
-            for (int i = tid; i < N; i += ZP) dst[i] = (float)__ldcs(src + i);
+            for (int i = tid; i < N; i += NT) dst[i] = (float)__ldcs(src + i);
         }
     }
     // the quantiser of :5481-5500 for one value
@@ -227,13 +237,30 @@ struct ImsH2 {
         return sign ? -ival : ival;
     }
 
-    // outputs of frame f = half `h` of the posteriors (the whole CTA calls this)
-    static __device__ __forceinline__ void emit(const FrameIO& io, const unsigned* soft2, int* s_misc, int f, int h, int ret, int tid, bool active)
+    // clear half `keep ^ 0xffffffff` of N consecutive tensor-memory columns, 16 at a time
+    template <int NC, int OFF = 0>
+    static __device__ __forceinline__ void tmem_mask_n(unsigned t, unsigned keep)
+    {
+        if constexpr (OFF < NC) {
+            constexpr int P = tmem_chunk(NC - OFF);
+            unsigned r[P];
+            TmemRow<P>::ld(t + OFF, r);
+            tmem_wait_ld<P>(r);
+#pragma unroll
+            for (int i = 0; i < P; i++) r[i] &= keep;
+            TmemRow<P>::st(t + OFF, r);
+            tmem_mask_n<NC, OFF + P>(t, keep);
+        }
+    }
+
+    // outputs of frame f = half `h` of the posteriors `gsoft` of its group (the whole CTA calls this)
+    static __device__ __noinline__ void emit(const FrameIO& io, const unsigned* gsoft, int* s_misc, int f, int h, int ret, int tid)
     {
         if (io.post) {
-            for (int col = 0; col < C; col++)
-                if (ALL_ACTIVE || active)
-                    ((short*)io.post)[(size_t)f * N + col * Z + tid] = (short)(int)h2_get(soft2[col * CS + tid + K::rt_ri()[col]], h);
+            for (int i = tid; i < N; i += NT) {
+                const int col = i / Z, p = i - col * Z;
+                ((short*)io.post)[(size_t)f * N + i] = (short)(int)h2_get(gsoft[col * CS + p + K::rt_ri()[col]], h);
+            }
         }
         const int lane = tid & 31;
         const unsigned sbit = h ? 0x80000000u : 0x8000u;
@@ -241,11 +268,11 @@ struct ImsH2 {
         constexpr int NROUND = (N + 31) & ~31;
         if (tid == 0) { s_misc[1] = 0; s_misc[2] = 0; }
         __syncthreads();
-        for (int i = tid; i < NROUND; i += ZP) {
+        for (int i = tid; i < NROUND; i += NT) {
             int bit = 0;
             if (i < N) {
                 const int col = i / Z, p = i - col * Z;
-                bit = (soft2[col * CS + p + K::rt_ri()[col]] & sbit) != 0u;
+                bit = (gsoft[col * CS + p + K::rt_ri()[col]] & sbit) != 0u;
             }
             const unsigned w = __ballot_sync(0xffffffffu, bit);
             if (lane == 0) {
@@ -277,17 +304,52 @@ struct ImsH2 {
         __syncthreads();
     }
 
+    // Put the next frame of the batch into half `h` of group `gs` (the whole CTA calls this, between iterations): fp32 LLRs
+    // staged in the group's posterior area, quantised (:5472-5500, coef from the energy pre-pass of channel.cu) into its half of
+    // the channel words, its half of the group's message words cleared (dcs[] = 0, :5463-5502).  -> frame index, or -1 when
+    // the batch is exhausted (the slot then keeps its old, bounded contents).
+    static __device__ __noinline__ int refill(const FrameIO& io, const MsSpecParams& sp, unsigned* soft2, int* s_misc, unsigned trow, int gs, int h, int tid)
+    {
+        __syncthreads();
+        if (tid == 0) s_misc[0] = (int)atomicAdd(io.next_frame, 1u);
+        __syncthreads();
+        const int f = s_misc[0];
+        if (f >= io.nf) return -1;
+        unsigned* gsoft = soft2 + gs * GROUP_WORDS;
+        unsigned* gy = gsoft + Y_OFF;
+        float* stage = (float*)gsoft;
+        load_frame(io, f, stage, tid);
+        const unsigned keep = h ? 0x0000ffffu : 0xffff0000u;
+        tmem_wait_st();                                                            // the last pass C's messages are in place
+        if (tid / ZP == gs) tmem_mask_n<E>(trow, keep);
+        __syncthreads();
+        const bool f64 = !io.ch.enabled && io.llr_dtype == 0;                       // doubles are quantised as doubles, not through fp32
+        const double* src = f64 ? (const double*)io.llr + (size_t)f * N : nullptr;
+        const double coef = io.coef[f];
+        for (int i = tid; i < N; i += NT) {
+            const int q = quantise(src ? src[i] : (double)stage[i], coef, sp);
+            const unsigned hv = h2_pack((float)(q - sp.max_data), 0.0f) & 0xffffu;    // iy - max_data: pass B
+            gy[i] = (gy[i] & keep) | (h ? hv << 16 : hv);
+            if (io.aux) io.aux[(size_t)f * N + i] = (short)q;
+        }
+        tmem_wait_st();
+        __syncthreads();
+        return f;
+    }
+
     static __device__ __forceinline__ void kernel(const FrameIO& io, const MsSpecParams& sp)
     {
         extern __shared__ __align__(16) unsigned soft2u[];
         unsigned* soft2 = soft2u;
-        unsigned* y = soft2 + Y_OFF;                             // quantised channel values, bit order, {frame 2p+1, frame 2p}
-        int* s_misc = (int*)(soft2 + MISC_OFF);
+        int* s_misc = (int*)(soft2 + MISC_OFF);                  // [0] frame ticket, [1..2] error counts, [4 .. 4+S) parity flags
         const int tid = threadIdx.x;
-        const bool active = tid < Z;
+        const int g = G == 1 ? 0 : tid / ZP, tg = tid - g * ZP;  // group, thread within the group = check row lane
+        const bool active = tg < Z;
         const bool lane0 = (tid & 31) == 0;
         const bool noexit = io.flags & 8u;                       // LDPCB200_NO_EARLY_EXIT
-        unsigned* softn = soft2 + tid;
+        unsigned* gsoft = soft2 + g * GROUP_WORDS;
+        unsigned* gy = gsoft + Y_OFF;
+        unsigned* softn = gsoft + tg;
         const unsigned mbar = (unsigned)__cvta_generic_to_shared(soft2 + MBAR_OFF);
         unsigned ph = 0;
 
@@ -314,75 +376,79 @@ struct ImsH2 {
                          :: "r"((unsigned)__cvta_generic_to_shared(s_misc)), "r"((unsigned)TCOLS) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
+        for (int i = tid; i < G * GROUP_WORDS; i += NT) soft2[i] = 0u;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned tbase = *(volatile unsigned*)s_misc;
+        // this thread's lane (bits 31:16: 32 * (warp mod 4) + lane) and first column (warps 4c .. 4c+3 own columns c E ..)
         const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * E), 0);
-        const int npairs = (io.nf + 1) >> 1;
+        tmem_zero_n<E>(trow);
+        tmem_wait_st();
+        __syncthreads();
+        if (tid < S) s_misc[4 + tid] = 0;
 
-        for (;;) {
-            __syncthreads();
-            if (tid == 0) s_misc[0] = (int)atomicAdd(io.next_frame, 1u);
-            __syncthreads();
-            const int pair = s_misc[0];
-            if (pair >= npairs) break;
-            const int fa = 2 * pair, fb = 2 * pair + 1 < io.nf ? 2 * pair + 1 : fa;       // an odd last frame rides in both halves
-            const bool twins = fb == fa;
-
-            // ---- first load: the two frames' fp32 LLRs into the (still unused) posterior area, then the quantiser
-            float* stage = (float*)soft2;
-            load_frame(io, fa, stage, tid);
-            if (!twins) load_frame(io, fb, stage + N, tid);
-            tmem_zero_n<E>(trow);                                                    // dcs[] = 0, :5463-5502
-            tmem_wait_st();
-            __syncthreads();
-            {
-                // per-frame energy normalisation (:5472-5479): coef comes from the energy pre-pass (channel.cu ims_energy_kernel)
-                const bool f64 = !io.ch.enabled && io.llr_dtype == 0;               // doubles are quantised as doubles, not through fp32
-                const double* sa = f64 ? (const double*)io.llr + (size_t)fa * N : nullptr;
-                const double* sb = f64 ? (const double*)io.llr + (size_t)fb * N : nullptr;
-                const double ca = io.coef[fa], cb = io.coef[fb];
-                for (int i = tid; i < N; i += ZP) {
-                    const int qa = quantise(sa ? sa[i] : (double)stage[i], ca, sp);
-                    const int qb = twins ? qa : quantise(sb ? sb[i] : (double)stage[N + i], cb, sp);
-                    y[i] = h2_pack((float)(qa - sp.max_data), (float)(qb - sp.max_data));       // iy - max_data: pass B
-                    if (io.aux) {
-                        io.aux[(size_t)fa * N + i] = (short)qa;
-                        if (!twins) io.aux[(size_t)fb * N + i] = (short)qb;
-                    }
+        if (io.maxiter <= 0) {
+            // no pass runs: decisions and "posteriors" are the quantised channel values, the return value is 0
+            for (;;) {
+                const int f = refill(io, sp, soft2, s_misc, trow, 0, 0, tid);
+                if (f < 0) break;
+                for (int i = tid; i < N; i += NT) {
+                    const int col = i / Z, p = i - col * Z;
+                    int q = p + K::rt_rot()[col];
+                    if (q >= Z) q -= Z;
+                    const unsigned w = h2_add(soft2[Y_OFF + col * Z + q], k.cap);
+                    soft2[col * CS + p] = w; soft2[col * CS + p + Z] = w;
                 }
                 __syncthreads();
+                emit(io, soft2, s_misc, f, 0, 0, tid);
             }
-
-            int reta = 0, retb = 0, pa = 1, pb = 1, iter;
-            bool seta = false, setb = false, donea = false, doneb = twins;
-            for (iter = 0; iter < io.maxiter; iter++) {
+        } else {
+            int sf[S], sit[S], sret[S];
+            bool sset[S];
+            int live = 0;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                sf[s] = refill(io, sp, soft2, s_misc, trow, s >> 1, s & 1, tid);
+                sit[s] = 0; sret[s] = 0; sset[s] = false;
+                live += sf[s] >= 0;
+            }
+            while (live > 0) {
                 tmem_wait_st();
                 passA<0>(softn, trow, mbar, ph, lane0, active, k);                               // STATE 1
-                if (ALL_ACTIVE || active) passB<0>(softn, y, tid, k);                            // STATE 2
+                if (ALL_ACTIVE || active) passB<0>(softn, gy, tg, k);                            // STATE 2
                 __syncthreads();
                 unsigned bad = 0;                                                                // STATE 3
                 passC<0>(softn, trow, k, bad);
                 if (!(ALL_ACTIVE || active)) bad = 0;
-                pa = __syncthreads_or((int)((bad >> 15) & 1u));
-                pb = __syncthreads_or((int)(bad >> 31));
-                if (!pa && !seta) { reta = iter + 1; seta = true; if (!noexit) { emit(io, soft2, s_misc, fa, 0, reta, tid, active); donea = true; } }
-                if (!pb && !setb) { retb = iter + 1; setb = true; if (!noexit && !twins) { emit(io, soft2, s_misc, fb, 1, retb, tid, active); doneb = true; } }
-                if (!noexit && donea && doneb) break;                                            // :5680-5685
-            }
-            if (io.maxiter <= 0) {                                                               // no pass ran: decisions of the channel values
-                for (int col = 0; col < C; col++)
-                    if (ALL_ACTIVE || active) {
-                        int p = tid + K::rt_rot()[col];
-                        if (p >= Z) p -= Z;
-                        const unsigned w = h2_add(y[col * Z + p], k.cap);
-                        softn[col * CS] = w; softn[col * CS + Z] = w;
-                    }
+                const bool b0 = __any_sync(0xffffffffu, (bad >> 15) & 1u), b1 = __any_sync(0xffffffffu, bad >> 31);
+                if (lane0) { if (b0) s_misc[4 + 2 * g] = 1; if (b1) s_misc[4 + 2 * g + 1] = 1; }
                 __syncthreads();
+                int par[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) par[s] = s_misc[4 + s];
+                __syncthreads();
+                if (tid < S) s_misc[4 + tid] = 0;
+                bool fin[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    fin[s] = false;
+                    if (sf[s] < 0) continue;
+                    sit[s]++;
+                    if (!par[s] && !sset[s]) { sret[s] = sit[s]; sset[s] = true; }               // :5680-5685
+                    if ((!par[s] && !noexit) || sit[s] >= io.maxiter) {
+                        emit(io, soft2 + (s >> 1) * GROUP_WORDS, s_misc, sf[s], s & 1, sset[s] ? sret[s] : -sit[s], tid);   // :5689
+                        fin[s] = true;
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if (fin[s]) {
+                        sf[s] = refill(io, sp, soft2, s_misc, trow, s >> 1, s & 1, tid);
+                        sit[s] = 0; sret[s] = 0; sset[s] = false;
+                        live -= sf[s] < 0;
+                    }
             }
-            if (!donea) emit(io, soft2, s_misc, fa, 0, seta ? reta : (pa ? -iter : iter + 1), tid, active);   // :5689
-            if (!doneb) emit(io, soft2, s_misc, fb, 1, setb ? retb : (pb ? -iter : iter + 1), tid, active);
         }
 
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -50,11 +50,11 @@ size_t ms_tmem_smem_bytes(int c, int Z, bool is_int)
 }
 
 // shared memory of ImsH2<K> (ims_h2.cuh, SMEM_WORDS)
-size_t ims_h2_smem_bytes(int c, int Z)
+size_t ims_h2_smem_bytes(int c, int Z, int groups)
 {
     const size_t y_off = 2 * (size_t)c * Z, n = (size_t)c * Z;
-    const size_t mbar = (y_off + n + 1) & ~(size_t)1;
-    return sizeof(float) * (mbar + 2 + 8);
+    const size_t group = (y_off + n + 1) & ~(size_t)1;
+    return sizeof(float) * (groups * group + 2 + 16);
 }
 
 size_t lms_tmem_pad_smem(size_t smem, int minb)
@@ -68,7 +68,7 @@ struct SpecEntry {
     const char* name;
     const void* kernel;
     int kind;                       // 0 LMS_DEC, 1 MS_DEC fp32, 2 IMS_DEC; 3 / 4 / 5 = LMS_DEC / MS_DEC / IMS_DEC with the messages in tensor memory;
-                                    // 6 = LMS_DEC, tensor memory, two frames per CTA (lms_tmem2.cuh); 7 = IMS_DEC, tensor memory, two frames per CTA as fp16 pairs (ims_h2.cuh)
+                                    // 6 = LMS_DEC, tensor memory, two frames per CTA (lms_tmem2.cuh); 7 / 8 = IMS_DEC, tensor memory, frames as fp16 pairs, one / two groups per CTA (ims_h2.cuh; zp = threads per CTA)
     int b, c, Z, E, zp, minb, maxdeg;
     const int *rp, *col, *sh;       // host copies for matching
 };
@@ -95,6 +95,7 @@ struct SpecRegistrar {
 #define LDPC_MS_SPEC_KIND_imst 5
 #define LDPC_MS_SPEC_KIND_lmst2 6
 #define LDPC_MS_SPEC_KIND_imsh 7
+#define LDPC_MS_SPEC_KIND_imsh2 8
 #define LDPC_MS_SPEC_REGISTER(KIND, NAME, B_, C_, Z_, E_, ZP_, MINB_)                                          \
     static ldpcb200::SpecRegistrar reg_##NAME(ldpcb200::SpecEntry{#NAME, (const void*)KIND##_spec_##NAME, LDPC_MS_SPEC_KIND_##KIND, B_, C_, Z_, E_, ZP_, MINB_, ldpcb200::gen_##NAME::Code::MAXDEG, \
         ldpcb200::gen_##NAME::Code::RP, ldpcb200::gen_##NAME::Code::COL, ldpcb200::gen_##NAME::Code::SH});
@@ -130,12 +131,12 @@ void lms_spec_aot_info(int idx, const char** name, int* threads, int* minb, size
         else if (e.kind == 3) *smem = lms_tmem_smem_bytes(e.b, e.c, e.Z, e.maxdeg);
         else if (e.kind == 6) *smem = lms_tmem2_smem_bytes(e.b, e.c, e.Z, e.maxdeg);
         else if (e.kind == 4 || e.kind == 5) *smem = ms_tmem_smem_bytes(e.c, e.Z, e.kind == 5);
-        else if (e.kind == 7) *smem = ims_h2_smem_bytes(e.c, e.Z);
+        else if (e.kind == 7 || e.kind == 8) *smem = ims_h2_smem_bytes(e.c, e.Z, e.kind - 6);
         else *smem = ms_spec_smem_bytes(e.c, e.Z);
         // tensor-memory variant: exactly `minb` CTAs may share an SM (their TMEM columns add up to 512; one more
         // resident CTA would sit in tcgen05.alloc until another exits), so the request is padded until minb + 1
         // no longer fit into the 228 KB of an sm_100 SM
-        if ((e.kind >= 3 && e.kind <= 5) || e.kind == 7) *smem = lms_tmem_pad_smem(*smem, e.minb);
+        if ((e.kind >= 3 && e.kind <= 5) || e.kind == 7 || e.kind == 8) *smem = lms_tmem_pad_smem(*smem, e.minb);
     }
 }
 

@@ -109,7 +109,7 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
       << ", MAXDEG = " << g.maxdeg << ";\n";
     // variant 0: doubled columns, all check state in registers; 1: single copy, sign/position words in shared memory;
     // 2: columns in the rotation of their last writer, c2v messages in tensor memory (lms_tmem.cuh); 3: the same, two frames per CTA (lms_tmem2.cuh);
-    // 4: IMS_DEC only, tensor memory, two frames per CTA as fp16 pairs (ims_h2.cuh)
+    // 4 / 5: IMS_DEC only, tensor memory, frames as fp16 pairs, one / two groups of zp threads per CTA (ims_h2.cuh)
     o << "    static constexpr bool DOUBLED = " << (variant != 1 ? "true" : "false") << ", PS_SMEM = " << (variant != 1 ? "false" : "true") << ";\n";
     o << "    static constexpr int TCOLS = " << tcols << ";\n";
     put_array(o, "    static constexpr int DELTA", delta, g.E);
@@ -147,8 +147,9 @@ std::string lms_spec_generate(const QcHost& g, int zp, int minb, int variant, in
         o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io)\n";
         o << "{ ldpcb200::" << (variant == 3 ? "LmsTmem2" : variant == 2 ? "LmsTmem" : "LmsSpec") << "<ldpcb200::gen_jit::Code>::kernel(io); }\n";
     } else {
-        o << "extern \"C\" __global__ void __launch_bounds__(" << zp << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)\n";
-        if (variant == 4) o << "{ ldpcb200::ImsH2<ldpcb200::gen_jit::Code>::kernel(io, sp); }\n";      // IMS_DEC, two frames per CTA as fp16 pairs (ims_h2.cuh)
+        const int groups = variant == 5 ? 2 : 1;          // ims_h2.cuh: groups of zp threads per CTA
+        o << "extern \"C\" __global__ void __launch_bounds__(" << (variant >= 4 ? groups * zp : zp) << ", " << minb << ") spec_jit(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)\n";
+        if (variant >= 4) o << "{ ldpcb200::ImsH2<ldpcb200::gen_jit::Code, " << groups << ">::kernel(io, sp); }\n";      // IMS_DEC, frames as fp16 pairs (ims_h2.cuh)
         else o << "{ ldpcb200::" << (variant == 2 ? "MsTmem" : "MsSpec") << "<ldpcb200::gen_jit::Code, " << (kind == 2 ? "true" : "false") << ">::kernel(io, sp); }\n";
     }
     return o.str();

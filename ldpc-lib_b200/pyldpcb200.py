@@ -165,7 +165,7 @@ class Decoder:
         if d["fast"] == 1 and self.decoder_id == ASP_DEC:
             d["name"] = "asp_fast_kernel (table-driven, double, messages in tensor memory)"
         if "%s" in d["name"]:
-            d["name"] %= {LMS_DEC: ("lms_tmem2" if d["two_frames"] else "lms_tmem") if d["tmem"] else "lms_spec", MS_DEC: "ms_tmem<float>" if d["tmem"] else "ms_spec<float>", IMS_DEC: ("ims_h2 (two frames per CTA as fp16 pairs)" if d["frames_per_cta"] == 2 else "ms_tmem<int>") if d["tmem"] else "ms_spec<int>"}.get(self.decoder_id, "spec")
+            d["name"] %= {LMS_DEC: ("lms_tmem2" if d["two_frames"] else "lms_tmem") if d["tmem"] else "lms_spec", MS_DEC: "ms_tmem<float>" if d["tmem"] else "ms_spec<float>", IMS_DEC: ("ims_h2 (frames as fp16 pairs, %d in flight per CTA)" % d["frames_per_cta"] if d["frames_per_cta"] >= 2 else "ms_tmem<int>") if d["tmem"] else "ms_spec<int>"}.get(self.decoder_id, "spec")
         return d
 
     def post_dtype(self):

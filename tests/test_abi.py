@@ -190,6 +190,20 @@ def test_bench_kernel_sass_uses_tensor_memory_and_stays_within_its_instruction_b
         assert abs(committed["per_edge"][k] - v) < 1e-9, (k, v, committed["per_edge"][k], "run `make -C ldpc-lib_b200 sassmix`")
 
 
+def test_every_kernel_family_compiles_at_run_time_without_a_gpu():
+    """The run-time generator + NVRTC for the flooding min-sum families too (spec_jit.cpp kinds 1 / 2: ms_spec, ms_tmem and the
+    fp16-pair IMS_DEC kernel with one and two groups per CTA) -- NVRTC is stricter than nvcc (no host functions, no headers)."""
+    import shutil
+    import subprocess
+    if not (os.path.exists("/usr/local/cuda/lib64/libnvrtc.so.12") or shutil.which("nvcc")):
+        pytest.skip("NVRTC not installed")
+    for check in ("1,0,2", "2,0,2", "1,2,2", "2,2,2", "2,4,4", "2,5,2"):
+        code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); from conftest import load_binding; from codes import load_code; "
+                "L = load_binding(); hd, _ = load_code('c4_wifi_12x24'); assert L.jit_check(hd, 81) > 10000" % (os.path.join(ROOT, "tests"), ROOT))
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LDPCB200_JIT_CHECK=check), capture_output=True, text=True)
+        assert r.returncode == 0, (check, r.stderr[-2000:])
+
+
 def test_jit_defines_reach_the_run_time_compilation():
     """LDPCB200_JIT_DEFINES (development switch): macro definitions handed to NVRTC change the kernel
     that is built -- here lms_tmem's doubled-column layout with the split mbarrier instead of the padded two-buffer (PP)

@@ -27,19 +27,21 @@ def test_deinterleaved_llrs_equal_the_reference_permutation_of_the_transmitted_o
         if mod >= 2 and N % (2 * mod):
             continue
         for punct in (0, 2):
+            ps = N - punct * Z
             with ldpc.Decoder(hd, Z, po.LMS, precision=32, use_fast=1) as d:
-                sent = d.generate_llr(2.0, 5, modulation=mod, punct=0, seed=7, dtype=np.float64)      # transmitted order
+                # transmitted order; sigma depends on the punctured blocks (bp_simulation.cpp:444), so the same `punct`, whose
+                # own puncturing overwrites the last positions of THIS buffer: those are left out of the comparison below
+                sent = d.generate_llr(2.0, 5, modulation=mod, punct=punct, seed=7, dtype=np.float64)
                 d.set_interleaver(direct, inverse)
                 got = d.generate_llr(2.0, 5, modulation=mod, punct=punct, seed=7, dtype=np.float64)
                 d.set_interleaver()
-                back = d.generate_llr(2.0, 5, modulation=mod, punct=0, seed=7, dtype=np.float64)
-            want = sent[:, inverse]                                  # y[i] = buffer[inverse[i]], bp_simulation.cpp:684
-            if punct:
-                want[:, N - punct * Z:] = 0.5                        # :697-710, after the inverse permutation
-            assert np.array_equal(got, want), (code, Z, mod, mode, punct)
+                back = d.generate_llr(2.0, 5, modulation=mod, punct=punct, seed=7, dtype=np.float64)
+            known = np.flatnonzero((inverse < ps) & (np.arange(N) < ps))     # y[i] = buffer[inverse[i]], bp_simulation.cpp:684
+            assert np.array_equal(got[:, known], sent[:, inverse[known]]), (code, Z, mod, mode, punct)
+            assert punct == 0 or np.all(got[:, ps:] == 0.5)                  # :697-710, after the inverse permutation
             assert np.array_equal(back, sent)
             if mode and mod >= 2:
-                assert not np.array_equal(got[:, :N - punct * Z], sent[:, :N - punct * Z])
+                assert not np.array_equal(got[:, :ps], sent[:, :ps])
 
 
 FAMILIES = [("LMS", 32, 1, "ref32x16_b", 126, 3, {}),             # lms_tmem (AOT), QAM-64

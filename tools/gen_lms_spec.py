@@ -4,7 +4,7 @@ matrix as compile-time tables plus the extern "C" kernel entry.  Used at build t
 matrices (ldpc-lib_b200/Makefile -> build/lms_spec_aot_gen.h); the library's run-time generator (spec_jit.cpp)
 emits the same text for any other code.
 
-    python tools/gen_lms_spec.py NAME=configs/file.jsonx:Z[:MINB[:lms|lmst|lmst2|ms|ims|mst|imst|imsh]] ... > out.h
+    python tools/gen_lms_spec.py NAME=configs/file.jsonx:Z[:MINB[:lms|lmst|lmst2|ms|ims|mst|imst|imsh|imsh2]] ... > out.h
 """
 import os
 import re
@@ -121,10 +121,11 @@ def emit(name, hd, Z, minb, kind="lms"):
         out.append('extern "C" __global__ void __launch_bounds__(%d, %d) %s_spec_%s(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)' % (zp, minb, kind, name))
         out.append("{ ldpcb200::MsTmem<ldpcb200::gen_%s::Code, %s>::kernel(io, sp); }" % (name, "true" if kind == "imst" else "false"))
         out.append("LDPC_MS_SPEC_REGISTER(%s, %s, %d, %d, %d, %d, %d, %d)" % (kind, name, b, c, Z, E, zp, minb))
-    elif kind == "imsh":
-        out.append('extern "C" __global__ void __launch_bounds__(%d, %d) imsh_spec_%s(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)' % (zp, minb, name))
-        out.append("{ ldpcb200::ImsH2<ldpcb200::gen_%s::Code>::kernel(io, sp); }" % name)
-        out.append("LDPC_MS_SPEC_REGISTER(imsh, %s, %d, %d, %d, %d, %d, %d)" % (name, b, c, Z, E, zp, minb))
+    elif kind in ("imsh", "imsh2"):                         # IMS_DEC as fp16 pairs: one or two groups of zp threads per CTA
+        groups = 2 if kind == "imsh2" else 1
+        out.append('extern "C" __global__ void __launch_bounds__(%d, %d) %s_spec_%s(const __grid_constant__ ldpcb200::FrameIO io, const ldpcb200::MsSpecParams sp)' % (groups * zp, minb, kind, name))
+        out.append("{ ldpcb200::ImsH2<ldpcb200::gen_%s::Code, %d>::kernel(io, sp); }" % (name, groups))
+        out.append("LDPC_MS_SPEC_REGISTER(%s, %s, %d, %d, %d, %d, %d, %d)" % (kind, name, b, c, Z, E, groups * zp, minb))
     elif kind == "lms":
         out.append('extern "C" __global__ void __launch_bounds__(%d, %d) lms_spec_%s(const __grid_constant__ ldpcb200::FrameIO io)' % (zp, minb, name))
         out.append("{ ldpcb200::LmsSpec<ldpcb200::gen_%s::Code>::kernel(io); }" % name)
