@@ -40,10 +40,17 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(unsigned int c0, unsigne
 // two N(0,1) samples from two 32-bit words
 __device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, float& z0, float& z1)
 {
+    // The transcendental steps use the special-function unit directly (lg2 / sqrt / sin / cos .approx: about 1e-6 absolute
+    // on a unit-variance sample, far below anything a Monte-Carlo estimate resolves) -- with libm's logf / sincospif the
+    // generator was a tenth of a whole decode.  Every path (fused first loads, ldpcb200_generate_llr, the IMS energy
+    // pre-pass) shares this function, so buffers handed to the reference are still the values the decoder sees.
     float u = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) / 2^32
-    float r = sqrtf(__fmul_rn(-2.0f, logf(u)));
-    float s, c;
-    sincospif(__fmul_rn(__uint2float_rn(b), 4.656612873077393e-10f), &s, &c);                     // angle = 2 pi b / 2^32
+    float l2, r, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(l2, -1.3862943611198906f)));     // sqrt(-2 ln u), ln u = lg2 u * ln 2
+    const float ang = __fmul_rn(__int2float_rn((int)b), 1.4629180792671596e-09f);                 // 2 pi b / 2^32 with b read as signed: [-pi, pi)
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
     z0 = __fmul_rn(r, c);
     z1 = __fmul_rn(r, s);
 }

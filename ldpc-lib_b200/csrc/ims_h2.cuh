@@ -142,23 +142,47 @@ struct ImsH2 {
             softC_load<J, Q + 1>(softn, rs);
         }
     }
-    // m[q] = min(cap, min over p != q of |v[p]|): prefix / suffix minima, 3 DEG - 4 two-input minima for both frames
+    // m[q] = min(cap, min over p != q of |v[p]|), both frames at once: groups of three edges, one three-input minimum per group
+    // (two dependent min.f16x2 become one VHMNMX), a "rest" term per group (the other groups and the ceiling) and one
+    // three-input minimum per edge over its two group mates and the rest -- lms_tmem.cuh min_of_others on fp16 pairs
+    static __device__ __forceinline__ unsigned min3(unsigned a, unsigned b, unsigned c) { return h2_min(h2_min(a, b), c); }
     template <int DEG>
     static __device__ __forceinline__ void min_of_others(const unsigned (&v)[DEG], unsigned (&m)[DEG], unsigned cap)
     {
-        if constexpr (DEG == 1) m[0] = cap;
+        constexpr int NG = (DEG + 2) / 3;
+        unsigned a[DEG], g[NG], rest[NG];
+#pragma unroll
+        for (int q = 0; q < DEG; q++) a[q] = h2_abs(v[q]);
+#pragma unroll
+        for (int k = 0; k < NG; k++) {
+            const int i = 3 * k;
+            g[k] = i + 2 < DEG ? min3(a[i], a[i + 1], a[i + 2]) : i + 1 < DEG ? h2_min(a[i], a[i + 1]) : a[i];
+        }
+        if constexpr (NG == 1) rest[0] = cap;
+        else if constexpr (NG == 2) { rest[0] = h2_min(g[1], cap); rest[1] = h2_min(g[0], cap); }
+        else if constexpr (NG == 3) { rest[0] = min3(g[1], g[2], cap); rest[1] = min3(g[0], g[2], cap); rest[2] = min3(g[0], g[1], cap); }
         else {
-            unsigned pre[DEG], suf[DEG];                         // pre[i] = min(cap, |v[0..i]|), suf[i] = min(cap, |v[i..]|)
-            pre[0] = h2_min(h2_abs(v[0]), cap);
-            suf[DEG - 1] = h2_min(h2_abs(v[DEG - 1]), cap);
+            unsigned pre[NG], suf[NG];                           // minima of the groups before / after group k
+            pre[0] = cap; suf[NG - 2] = g[NG - 1];
 #pragma unroll
-            for (int i = 1; i < DEG - 1; i++) pre[i] = h2_min(pre[i - 1], h2_abs(v[i]));
+            for (int k = 1; k < NG; k++) pre[k] = h2_min(pre[k - 1], g[k - 1]);
 #pragma unroll
-            for (int i = DEG - 2; i > 0; i--) suf[i] = h2_min(suf[i + 1], h2_abs(v[i]));
-            m[0] = suf[1];
-            m[DEG - 1] = pre[DEG - 2];
+            for (int k = NG - 3; k >= 0; k--) suf[k] = h2_min(suf[k + 1], g[k + 1]);
 #pragma unroll
-            for (int i = 1; i < DEG - 1; i++) m[i] = h2_min(pre[i - 1], suf[i + 1]);
+            for (int k = 0; k < NG - 1; k++) rest[k] = h2_min(pre[k], suf[k]);
+            rest[NG - 1] = pre[NG - 1];
+        }
+#pragma unroll
+        for (int k = 0; k < NG; k++) {
+            const int i = 3 * k;
+            if (i + 2 < DEG) {
+                m[i] = min3(a[i + 1], a[i + 2], rest[k]);
+                m[i + 1] = min3(a[i], a[i + 2], rest[k]);
+                m[i + 2] = min3(a[i], a[i + 1], rest[k]);
+            } else if (i + 1 < DEG) {
+                m[i] = h2_min(a[i + 1], rest[k]);
+                m[i + 1] = h2_min(a[i], rest[k]);
+            } else m[i] = rest[k];
         }
     }
     template <int J>
@@ -226,8 +250,8 @@ struct ImsH2 {
             for (int i = tid; i < N; i += NT) dst[i] = (float)__ldcs(src + i);
         }
     }
-    // the quantiser of :5481-5500 for one value
-    static __device__ __forceinline__ int quantise(double val, double coef, const MsSpecParams& sp)
+    // the quantiser of :5481-5500 for one value, in the reference's double arithmetic
+    static __device__ __noinline__ int quantise_exact(double val, double coef, const MsSpecParams& sp)
     {
         int sign = 0;
         if (val < 0) { val = -val; sign = 1; }
@@ -235,6 +259,17 @@ struct ImsH2 {
         if (val > sp.thr) val = sp.thr;
         const int ival = (short)floor(div_normal(val * sp.max_quant, sp.thr) + 0.5);   // the correctly rounded quotient without the slow-path branch (channel.cuh)
         return sign ? -ival : ival;
+    }
+    // The same value from an fp32 estimate whenever that cannot be wrong: t = |y| coef max_quant / thr is at most max_quant
+    // (<= 127), the estimate is within 1e-4 of it (a few fp32 roundings), so floor(t + 0.5) is decided unless t + 0.5 lies
+    // within 1e-3 of an integer -- one value in 500 -- and only then the double arithmetic runs.  cs = coef max_quant / thr.
+    static __device__ __forceinline__ int quantise(double val, float valf, double coef, float cs, const MsSpecParams& sp)
+    {
+        const float u = fminf(fabsf(valf) * cs, (float)sp.max_quant) + 0.5f;
+        const float fl = floorf(u), frac = u - fl;
+        if (!(frac >= 1e-3f && frac <= 1.0f - 1e-3f)) return quantise_exact(val, coef, sp);
+        const int ival = (int)fl;
+        return valf < 0.0f ? -ival : ival;
     }
 
     // clear half `keep ^ 0xffffffff` of N consecutive tensor-memory columns, 16 at a time
@@ -308,13 +343,16 @@ struct ImsH2 {
     // staged in the group's posterior area, quantised (:5472-5500, coef from the energy pre-pass of channel.cu) into its half of
     // the channel words, its half of the group's message words cleared (dcs[] = 0, :5463-5502).  -> frame index, or -1 when
     // the batch is exhausted (the slot then keeps its old, bounded contents).
-    static __device__ __noinline__ int refill(const FrameIO& io, const MsSpecParams& sp, unsigned* soft2, int* s_misc, unsigned trow, int gs, int h, int tid)
+    // Tickets are drawn one refill ahead (thread 0 carries the next one): the atomic issued here is only waited for when
+    // the function returns, behind the whole refill.  -> (frame, next ticket)
+    static __device__ __noinline__ int2 refill(const FrameIO& io, const MsSpecParams& sp, unsigned* soft2, int* s_misc, unsigned trow, int gs, int h, int tid, int ticket)
     {
         __syncthreads();
-        if (tid == 0) s_misc[0] = (int)atomicAdd(io.next_frame, 1u);
+        int next = 0;
+        if (tid == 0) { s_misc[0] = ticket; next = (int)atomicAdd(io.next_frame, 1u); }
         __syncthreads();
         const int f = s_misc[0];
-        if (f >= io.nf) return -1;
+        if (f >= io.nf) return make_int2(-1, next);
         unsigned* gsoft = soft2 + gs * GROUP_WORDS;
         unsigned* gy = gsoft + Y_OFF;
         float* stage = (float*)gsoft;
@@ -326,15 +364,16 @@ struct ImsH2 {
         const bool f64 = !io.ch.enabled && io.llr_dtype == 0;                       // doubles are quantised as doubles, not through fp32
         const double* src = f64 ? (const double*)io.llr + (size_t)f * N : nullptr;
         const double coef = io.coef[f];
+        const float cs = (float)(coef * sp.max_quant / sp.thr);
         for (int i = tid; i < N; i += NT) {
-            const int q = quantise(src ? src[i] : (double)stage[i], coef, sp);
+            const int q = src ? quantise(src[i], (float)src[i], coef, cs, sp) : quantise((double)stage[i], stage[i], coef, cs, sp);
             const unsigned hv = h2_pack((float)(q - sp.max_data), 0.0f) & 0xffffu;    // iy - max_data: pass B
             gy[i] = (gy[i] & keep) | (h ? hv << 16 : hv);
             if (io.aux) io.aux[(size_t)f * N + i] = (short)q;
         }
         tmem_wait_st();
         __syncthreads();
-        return f;
+        return make_int2(f, next);
     }
 
     static __device__ __forceinline__ void kernel(const FrameIO& io, const MsSpecParams& sp)
@@ -387,11 +426,15 @@ struct ImsH2 {
         tmem_wait_st();
         __syncthreads();
         if (tid < S) s_misc[4 + tid] = 0;
+        int ticket = 0;
+        if (tid == 0) ticket = (int)atomicAdd(io.next_frame, 1u);
 
         if (io.maxiter <= 0) {
             // no pass runs: decisions and "posteriors" are the quantised channel values, the return value is 0
             for (;;) {
-                const int f = refill(io, sp, soft2, s_misc, trow, 0, 0, tid);
+                const int2 rf = refill(io, sp, soft2, s_misc, trow, 0, 0, tid, ticket);
+                const int f = rf.x;
+                ticket = rf.y;
                 if (f < 0) break;
                 for (int i = tid; i < N; i += NT) {
                     const int col = i / Z, p = i - col * Z;
@@ -409,7 +452,8 @@ struct ImsH2 {
             int live = 0;
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                sf[s] = refill(io, sp, soft2, s_misc, trow, s >> 1, s & 1, tid);
+                const int2 rf = refill(io, sp, soft2, s_misc, trow, s >> 1, s & 1, tid, ticket);
+                sf[s] = rf.x; ticket = rf.y;
                 sit[s] = 0; sret[s] = 0; sset[s] = false;
                 live += sf[s] >= 0;
             }
@@ -444,7 +488,8 @@ struct ImsH2 {
 #pragma unroll
                 for (int s = 0; s < S; s++)
                     if (fin[s]) {
-                        sf[s] = refill(io, sp, soft2, s_misc, trow, s >> 1, s & 1, tid);
+                        const int2 rf = refill(io, sp, soft2, s_misc, trow, s >> 1, s & 1, tid, ticket);
+                        sf[s] = rf.x; ticket = rf.y;
                         sit[s] = 0; sret[s] = 0; sset[s] = false;
                         live -= sf[s] < 0;
                     }

@@ -371,13 +371,15 @@ FastPlan plan_lms_fast(const QcHost& g, int precision, int smem_per_sm, int smem
     bool two = false;
     if (!(no_spec && *no_spec == '1') && !(no_aot && *no_aot == '1' && allow_jit)) {
         const char* t2 = getenv("LDPCB200_TMEM2");          // 1: two frames per CTA (lms_tmem2.cuh; measured slower) instead of one (lms_tmem.cuh)
-        if (tmem && t2 && *t2 == '1') aot = find_lms_spec_aot(g, 6);
+        bool want_two = tmem && t2 && *t2 == '1';
+        if (want_two) aot = find_lms_spec_aot(g, 6);
         if (aot >= 0) { p.tmem = 2; two = true; }
+        else if (want_two && allow_jit) {}                  // no ahead-of-time two-frame instance: compile one below
         else if (tmem) {
             aot = find_lms_spec_aot(g, 3);                  // messages in tensor memory (lms_tmem.cuh)
             if (aot >= 0) p.tmem = 1;
         }
-        if (aot < 0) aot = find_lms_spec_aot(g, 0);
+        if (aot < 0 && !(want_two && allow_jit)) aot = find_lms_spec_aot(g, 0);
     }
     if (aot >= 0) {                                          // a code-specialised instance exists for this matrix
         int minb = 1;

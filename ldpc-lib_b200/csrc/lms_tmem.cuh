@@ -897,12 +897,29 @@ struct LmsTmem {
         // (the shuffle tells the compiler that the address is warp-uniform: LDTM / STTM take it from a uniform register)
         const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * E), 0);
 
+        // Frame tickets are drawn two frames ahead (thread 0 keeps them in registers): the round trip of the atomic is off the
+        // path between two frames, and the NEXT frame's index is known early enough to pull its LLRs into L2 while this one
+        // is decoded (buffer mode; 128 bytes per prefetch).
+        int t_cur = 0, t_next = 0;
+        if (tid == 0) { t_cur = (int)atomicAdd(io.next_frame, 1u); t_next = (int)atomicAdd(io.next_frame, 1u); }
         for (;;) {
             __syncthreads();
-            if (tid == 0) { s_misc[0] = (int)atomicAdd(io.next_frame, 1u); s_misc[1] = 0; s_misc[2] = 0; }
+            if (tid == 0) {
+                s_misc[0] = t_cur; s_misc[3] = t_next; s_misc[1] = 0; s_misc[2] = 0;
+                t_cur = t_next;
+                t_next = (int)atomicAdd(io.next_frame, 1u);
+            }
             __syncthreads();
             const int f = s_misc[0];
             if (f >= io.nf) break;
+            if (!io.ch.enabled) {
+                const int fn = s_misc[3];
+                if (fn < io.nf) {
+                    const size_t fbytes = (size_t)N * (io.llr_dtype == 1 ? 4 : 8);
+                    const char* nb = (const char*)io.llr + (size_t)fn * fbytes;
+                    for (size_t o = (size_t)tid * 128; o < fbytes; o += (size_t)ZP * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(nb + o));
+                }
+            }
 
             bool packed = false;                                 // hb already holds the decisions of the channel values
             if (io.ch.enabled) {

@@ -32,6 +32,9 @@ def parse(text):
         if op == "BRA":
             t = re.search(r"0x([0-9a-f]+)", rest)
             tgt = int(t.group(1), 16) if t else None
+            u = re.match(r"(!?UP\d+)\s*,", rest)                 # BRA.U UP0, target: a branch on a uniform predicate
+            if u and not pred:
+                pred = u.group(1)
         out.append((addr, op, pred, tgt))
     return out
 
