@@ -169,7 +169,8 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
     } else if (use_fast && (h->decoder_id == LDPCB200_IMS_DEC || h->decoder_id == LDPCB200_MS_DEC)) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, (io.nf + h->fast.frames_per_cta - 1) / h->fast.frames_per_cta);   // ims_h2: frames in flight per CTA
         CU(launch_ms_fast(h->fast, h->dp, io, std::max(fgrid, 1), h->stream));
-    } else if (use_fast && (h->decoder_id == LDPCB200_TASP_DEC || h->decoder_id == LDPCB200_ASP_DEC || h->decoder_id == LDPCB200_LCHE_DEC || h->decoder_id == LDPCB200_IASP_DEC)) {
+    } else if (use_fast && (h->decoder_id == LDPCB200_TASP_DEC || h->decoder_id == LDPCB200_ASP_DEC || h->decoder_id == LDPCB200_LCHE_DEC || h->decoder_id == LDPCB200_IASP_DEC ||
+                            ((h->decoder_id == LDPCB200_BP_DEC || h->decoder_id == LDPCB200_SP_DEC) && !io.bp_syndrome))) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
         CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream));
     } else if (is_minsum(h->decoder_id)) {
@@ -322,7 +323,8 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
             else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ms_fast(h->g, 2, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
             else if (decoder_id == LDPCB200_MS_DEC && p.precision == 64) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);    // double: tasp_fast.cu
             else if (decoder_id == LDPCB200_MS_DEC) h->fast = plan_ms_fast(h->g, 1, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
-            else if (decoder_id == LDPCB200_TASP_DEC || decoder_id == LDPCB200_ASP_DEC || decoder_id == LDPCB200_LCHE_DEC || decoder_id == LDPCB200_IASP_DEC) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
+            else if (decoder_id == LDPCB200_TASP_DEC || decoder_id == LDPCB200_ASP_DEC || decoder_id == LDPCB200_LCHE_DEC || decoder_id == LDPCB200_IASP_DEC ||
+                     decoder_id == LDPCB200_BP_DEC || decoder_id == LDPCB200_SP_DEC) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
         }
         return 0;
     }();

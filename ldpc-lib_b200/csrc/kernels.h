@@ -31,6 +31,7 @@ struct FastPlan {
     int variant = 0;                    // 0 table-driven (lms_fast.cu), 1 code-specialised ahead of time, 2 run-time compiled
     int spec_index = -1;
     int tmem = 0;                       // 1: LMS_DEC with the c2v messages in tensor memory (lms_tmem.cuh)
+    int msg32 = 0;                      // BP_DEC / SP_DEC (tasp_fast.cu): messages rounded to fp32, one tensor-memory column each
     const void* jit_kernel = nullptr;
     std::string note;                   // why a faster variant was not used
     std::vector<unsigned char> tab;     // the kernel's parameter-space copy of the edge lists

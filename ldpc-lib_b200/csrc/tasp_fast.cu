@@ -8,6 +8,8 @@
 //   asp_fast_kernel              ASP_DEC   sum_prod_gf2_decod_qc_lm        decoders.cpp:2324-2581   flooding, probability domain, double
 //   iasp_fast_kernel             IASP_DEC  isum_prod_gf2_decod_qc_lm       decoders.cpp:3822-4121   flooding, 12-bit fixed point
 //   ms64_fast_kernel             MS_DEC    min_sum_decod_qc_lm             decoders.cpp:4554-4767   flooding normalised min-sum in DOUBLE
+//   bpsp_fast_kernel<.., false>  BP_DEC    bp_decod_qc_lm                  decoders.cpp:1708-1920   flooding, LLR domain (tanh rule), double
+//   bpsp_fast_kernel<.., true>   SP_DEC    sum_prod_decod_qc_lm            decoders.cpp:1923-2185   flooding, likelihood-ratio domain, double
 //
 // All in the reference's arithmetic and operation order (the expressions of the parity kernels in dec_sumprod.cu, which
 // they equal bit for bit: tests/test_gpu_tmem.py).  What makes them faster than the parity kernels (which keep
@@ -24,6 +26,7 @@
 #include "dec_common.cuh"
 #include "lms_spec.cuh"
 #include "lms_tmem.cuh"
+#include "fastmath64.cuh"
 
 namespace ldpcb200 {
 
@@ -889,6 +892,295 @@ __global__ void __launch_bounds__(MAXT, 1) ms64_fast_kernel(const TaspTab T, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// BP_DEC (bp_decod_qc_lm, decoders.cpp:1708-1920) and SP_DEC (sum_prod_decod_qc_lm, :1923-2185): the two flooding
+// sum-product decoders, float class of the parity bar (identical decisions and iteration counts on >= 99.99 % of frames,
+// posteriors within 1e-4 relative) -- so the expressions may be regrouped as long as they stay the reference's function.
+// Both on the ms64 skeleton: check-to-variable messages as two TMEM columns per edge and lane, posteriors and channel
+// values as doubles in shared memory, an iteration is
+//   S  per check row: syndrome of the current posteriors (flat loop, CTA-wide OR; :1742-1779 / :1865-1893, :1964-1987 / :2129-2149)
+//   C  per check row, no barriers: variable-to-check values of the row's edges from posterior and old message, the row's
+//      combination, the new messages (row function templated on the weight: everything in registers)
+//   A  block row by block row (barrier in between): posterior = channel value combined with the new messages of the bit, in
+//      ascending block-row order like :1834-1862 / :2103-2127 (the first edge of a column starts from the channel value).
+// BP_DEC.  The reference goes through the log domain: x_e = log|tanh(d_e / 2)| with d_e = soft - old message, s = sum x_e,
+// new message = +-log((1 + A) / (1 - A)), A = exp(s - x_e) (:1790-1862): two exp, two log and two divisions per edge.
+// exp(s - x_e) is the product of the other edges' |tanh|, so here T_e = |(e^d - 1) / (e^d + 1)| is kept as it is, S = prod T_e,
+// A = S / T_e: one exp, one log, three divisions per edge, the same function (a row with a T_e = 0 gives 0 / 0 = NaN for that
+// edge and 0 for the others exactly like exp(-inf - (-inf)) and exp(-inf) do, and the clamp turns NaN into +19.07 as the
+// reference's min / max expressions do).  The chained stale syndrome (LDPCB200_BP_CHAIN_SYNDROME, :1742-1759) stays on
+// the parity kernel, which runs the frames in order.
+// SP_DEC (likelihood-ratio domain, no exp / log inside the loop).  The reference forms the variable-to-check value as the
+// channel value times every OTHER message of the column (:2013-2040); here the column product P is kept per bit and the
+// edge's own message divided out -- with the count of exactly-zero messages kept beside P, because the clamp (:2118) does
+// produce zeros (a = -1) and a zero cannot be divided out.
+// A message of these two decoders as it sits in tensor memory: a double in two columns (W = 2), or rounded to fp32 in one
+// (W = 1: half the columns per frame, twice the frames per SM -- the kernels are latency-bound, and a message rounded to
+// 24 bits moves a posterior by up to 1e-5 relative in the tests, one order below the 1e-4 of the parity bar: opt-in,
+// LDPCB200_BPSP_MSG32=1; measured C4: BP_DEC 0.73 instead of 0.64 Gbit/s, SP_DEC 1.03 instead of 0.78)
+template <int W> __device__ __forceinline__ double bpsp_msg(const unsigned* lw, int q)
+{
+    if constexpr (W == 2) return __hiloint2double((int)lw[2 * q + 1], (int)lw[2 * q]);
+    else return (double)__uint_as_float(lw[q]);
+}
+template <int W> __device__ __forceinline__ void bpsp_put(unsigned* lw, int q, double m)
+{
+    if constexpr (W == 2) { lw[2 * q] = (unsigned)__double2loint(m); lw[2 * q + 1] = (unsigned)__double2hiint(m); }
+    else lw[q] = __float_as_uint((float)m);
+}
+
+template <int RW, int W>
+__device__ __noinline__ void bp_rowC(const double* A, const unsigned* etab, int e0, int n, int Z, unsigned trow)
+{
+    unsigned lw[W * RW];
+    tmem_ld_n<W * RW>(trow + (unsigned)(W * e0), lw);
+    double d[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        d[q] = A[(int)(pk & 0xffffu) + k];
+    }
+    tmem_wait_ld<W * RW>(lw);
+    double S = 1.0;
+    int bs = 0, bb[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double a = fx_exp(d[q] - bpsp_msg<W>(lw, q));    // :1797 (fastmath64.cuh: straight-line code)
+        bb[q] = a < 1;                                                                             // :1800
+        bs ^= bb[q];
+        const double t = div_normal(a - 1, a + 1);                                                 // :1798, |.| below
+        d[q] = t < 0 ? -t : t;
+        S *= d[q];                                                                                 // exp(sum of the logs), :1810
+    }
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double a = d[q] == 0.0 ? S / d[q] : div_normal(S, d[q]);                             // exp(s - x_e), :1843 (0 / 0 -> NaN like exp(NaN))
+        const double den = 1 - a;
+        const double r = den == 0.0 ? (1 + a) / den : div_normal(1 + a, den);                      // x / 0 must stay +inf
+        double m = (1 - 2 * (bs ^ bb[q])) * fx_log(r);                                             // :1846
+        m = tf_maxd(tf_mind(m, 19.07), -19.07);                                                    // :1847
+        bpsp_put<W>(lw, q, m);
+    }
+    tmem_st_n<W * RW>(trow + (unsigned)(W * e0), lw);
+}
+
+// posterior += new message (BP) in ascending block-row order; the first edge of a column starts from the channel value (:1832)
+template <int RW, int W>
+__device__ __noinline__ void bp_rowA(double* A, const double* y, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    unsigned lw[W * RW];
+    tmem_ld_n<W * RW>(trow + (unsigned)(W * e0), lw);
+    int idx[RW];
+    double acc[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        acc[q] = (pk >> 31) ? y[idx[q]] : A[idx[q]];
+    }
+    tmem_wait_ld<W * RW>(lw);
+#pragma unroll
+    for (int q = 0; q < RW; q++)
+        if (active) A[idx[q]] = acc[q] + bpsp_msg<W>(lw, q);   // :1857
+}
+
+// syndrome of one block row's check rows: XOR over the edges of (posterior < thr) -- thr = 0 (BP_DEC) or 1 (SP_DEC)
+__device__ __forceinline__ int bpsp_row_syndrome(const double* A, const unsigned* etab, int e0, int e1, int n, int Z, double thr)
+{
+    int synd = 0;
+    for (int e = e0; e < e1; e++) {
+        const unsigned pk = etab[e];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        synd ^= A[(int)(pk & 0xffffu) + k] < thr;
+    }
+    return synd;
+}
+
+// SP_DEC row: P = column products without exact zeros, zc = number of exact zeros among the column's messages
+template <int RW, int W>
+__device__ __noinline__ void sp_rowC(const double* P, const unsigned char* zc, const unsigned* etab, int e0, int n, int Z, unsigned trow)
+{
+    unsigned lw[W * RW];
+    tmem_ld_n<W * RW>(trow + (unsigned)(W * e0), lw);
+    double pr[RW], z0[RW];
+    int nz[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        pr[q] = P[(int)(pk & 0xffffu) + k];
+        nz[q] = zc[(int)(pk & 0xffffu) + k];
+    }
+    tmem_wait_ld<W * RW>(lw);
+    double S = 1.0;
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double own = bpsp_msg<W>(lw, q);
+        // the channel value times the OTHER messages of the column (:2022-2036)
+        double aa;
+        if (own == 0.0) aa = nz[q] == 1 ? pr[q] : 0.0;
+        else aa = nz[q] ? 0.0 : div_normal(pr[q], own);
+        z0[q] = div_normal(aa - 1, aa + 1);                                                        // :2038
+        S *= z0[q];                                                                                // :2044
+    }
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        // :2111-2112 with div_normal; the two places where IEEE semantics matter are kept: z0 = 0 makes S zero or NaN, so the
+        // quotient is NaN either way (-> 1.9e8 after the clamp), and x / 0 must be an infinity, not NaN
+        double a = z0[q] == 0.0 ? S / z0[q] : div_normal(S, z0[q]);
+        const double den = 1 - a;
+        a = den == 0.0 ? (1 + a) / den : div_normal(1 + a, den);
+        a = tf_maxd(tf_mind(a, 1.9e+8), -5.2e-9);                                                  // :2113
+        bpsp_put<W>(lw, q, a);
+    }
+    tmem_st_n<W * RW>(trow + (unsigned)(W * e0), lw);
+}
+
+// posterior *= new message (SP, :2115) in ascending block-row order, as (product of the non-zero factors, number of zeros)
+template <int RW, int W>
+__device__ __noinline__ void sp_rowA(double* P, unsigned char* zc, const double* y, const unsigned* etab, int e0, int n, int Z, bool active, unsigned trow)
+{
+    unsigned lw[W * RW];
+    tmem_ld_n<W * RW>(trow + (unsigned)(W * e0), lw);
+    int idx[RW], cnt[RW];
+    double acc[RW];
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const unsigned pk = etab[e0 + q];
+        int k = n + (int)((pk >> 16) & 0x7fffu);
+        if (k >= Z) k -= Z;
+        idx[q] = (int)(pk & 0xffffu) + k;
+        acc[q] = (pk >> 31) ? y[idx[q]] : P[idx[q]];
+        cnt[q] = (pk >> 31) ? 0 : zc[idx[q]];
+    }
+    tmem_wait_ld<W * RW>(lw);
+#pragma unroll
+    for (int q = 0; q < RW; q++) {
+        const double m = bpsp_msg<W>(lw, q);
+        if (active) {
+            if (m == 0.0) zc[idx[q]] = (unsigned char)(cnt[q] + 1);
+            else { zc[idx[q]] = (unsigned char)cnt[q]; P[idx[q]] = acc[q] * m; }
+            if (m == 0.0 && (etab[e0 + q] >> 31)) P[idx[q]] = acc[q];
+        }
+    }
+}
+
+// SP = false: BP_DEC, true: SP_DEC
+template <int MAXT, bool SP, int W>
+__global__ void __launch_bounds__(MAXT, 1) bpsp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
+{
+    extern __shared__ __align__(16) double tf_smem[];
+    const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
+    double* A = tf_smem;                 // posterior: BP_DEC LLR, SP_DEC product of the non-zero factors
+    double* y = A + N;                   // channel values: clamped LLR (:1738) / its exponential (:1947-1951)
+    unsigned* etab = (unsigned*)(y + N);
+    int* rpw = (int*)(etab + E);
+    unsigned* s_t = (unsigned*)(rpw + b + 1);
+    unsigned char* zc = (unsigned char*)(s_t + 4);       // SP_DEC: exact zeros among a bit's factors
+    const bool active = tid < Z;
+    const int n = active ? tid : Z - 1;
+    const bool noexit = io.flags & LDPCB200_NO_EARLY_EXIT;
+    const double thr = SP ? 1.0 : 0.0;
+
+    for (int e = tid; e < E; e += nt) {
+        const int c = g.col[e];
+        etab[e] = (unsigned)(c * Z) | ((unsigned)g.sh[e] << 16) | (g.cedge[g.cp[c]] == e ? 0x80000000u : 0u);
+    }
+    for (int j = tid; j <= b; j += nt) rpw[j] = g.rp[j];
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(s_t)), "r"((unsigned)T.tcols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = *(volatile unsigned*)s_t;
+    const unsigned trow = __shfl_sync(0xffffffffu, tbase + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)((tid >> 7) * W * E), 0);
+
+    // the posterior as the reference holds it (SP_DEC: a zero factor makes it zero)
+    auto post = [&](int i) -> double { if constexpr (SP) return zc[i] ? 0.0 : A[i]; else return A[i]; };
+    auto syndrome = [&]() -> int {
+        int bad = 0;
+        for (int j = 0; j < b; j++) {
+            int synd = 0;
+            for (int e = rpw[j]; e < rpw[j + 1]; e++) {
+                const unsigned pk = etab[e];
+                int k = n + (int)((pk >> 16) & 0x7fffu);
+                if (k >= Z) k -= Z;
+                synd ^= post((int)(pk & 0xffffu) + k) < thr;
+            }
+            bad |= synd;
+        }
+        return __syncthreads_or(active ? bad : 0);
+    };
+
+    for (;;) {
+        const int f = next_frame(io);
+        if (f >= io.nf) break;
+        for (int i = tid; i < N; i += nt) {
+            double v = tf_maxd(tf_mind(load_llr(io, N, f, i), 20.0), -20.0);                     // :1738 / :1947-1950
+            if constexpr (SP) { v = exp(v); zc[i] = 0; }
+            y[i] = v; A[i] = v;
+        }
+        {
+            // messages: BP_DEC 0 (:1732-1734), SP_DEC 1 (:1957-1959)
+            unsigned init[2] = { 0u, SP ? 0x3ff00000u : 0u };
+            if constexpr (W == 1) init[0] = SP ? 0x3f800000u : 0u;
+            for (int e = 0; e < E; e++) TmemRow<W>::st(trow + (unsigned)(W * e), init);
+            tmem_wait_st();
+        }
+        __syncthreads();
+        int ret = 0, iter = 0;
+        int parity = syndrome();                                                                 // :1742-1779 / :1964-1987
+        bool locked = !parity;                                                                   // return 0: the channel values are a codeword
+        while (iter < io.maxiter && (parity || noexit)) {
+            for (int j = 0; j < b; j++) {                                                        // sweep C
+                const int e0 = rpw[j];
+                switch (rpw[j + 1] - e0) {
+#define BP_C(k) case k: if constexpr (SP) sp_rowC<k, W>(A, zc, etab, e0, n, Z, trow); else bp_rowC<k, W>(A, etab, e0, n, Z, trow); break;
+                case 1: if constexpr (SP) sp_rowC<1, W>(A, zc, etab, e0, n, Z, trow); else bp_rowC<1, W>(A, etab, e0, n, Z, trow); break;
+                AF_CASES(BP_C)
+#undef BP_C
+                default: break;
+                }
+            }
+            tmem_wait_st();
+            __syncthreads();
+            for (int j = 0; j < b; j++) {                                                        // sweep A
+                const int e0 = rpw[j];
+                switch (rpw[j + 1] - e0) {
+#define BP_A(k) case k: if constexpr (SP) sp_rowA<k, W>(A, zc, y, etab, e0, n, Z, active, trow); else bp_rowA<k, W>(A, y, etab, e0, n, Z, active, trow); break;
+                case 1: if constexpr (SP) sp_rowA<1, W>(A, zc, y, etab, e0, n, Z, active, trow); else bp_rowA<1, W>(A, y, etab, e0, n, Z, active, trow); break;
+                AF_CASES(BP_A)
+#undef BP_A
+                default: break;
+                }
+                __syncthreads();
+            }
+            iter++;
+            const int par = syndrome();                                                          // :1865-1893 / :2129-2149
+            if (!locked) { parity = par; if (!par) { ret = iter; locked = true; } }
+        }
+        if (!locked) ret = -iter;                                                                // :1919 / :2184
+        for (int i = tid; i < N; i += nt) store_post(io, N, f, i, post(i));
+        emit_frame(g, io, f, ret, [&](int i) { return (int)(post(i) < thr); });
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)T.tcols) : "memory");
+    }
+}
+
 size_t lms_tmem_pad_smem(size_t smem, int minb);
 
 // decoder_id: LDPCB200_TASP_DEC, LDPCB200_LCHE_DEC, LDPCB200_ASP_DEC, LDPCB200_IASP_DEC, or LDPCB200_LMS_DEC / LDPCB200_MS_DEC (double)
@@ -899,7 +1191,8 @@ FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int sm
     if (off && *off == '1') return p;
     if (g.maxdeg > TASP_MAXDEG || g.N > 65535 || g.Z > 1024) return p;   // (row weight 1 only for MS_DEC: map_bin needs 2, the other row functions start at 2)
     const bool iasp = decoder_id == LDPCB200_IASP_DEC;
-    const bool ms = decoder_id == LDPCB200_MS_DEC;
+    const bool bpsp = decoder_id == LDPCB200_BP_DEC || decoder_id == LDPCB200_SP_DEC;
+    const bool ms = decoder_id == LDPCB200_MS_DEC || bpsp;               // row weight 1 allowed, two doubles per bit, every column needs an edge
     const bool asp = decoder_id == LDPCB200_ASP_DEC || iasp;
     if (!ms && g.mindeg < 2) return p;
     if (asp && g.all_cw_2) { p.note = "all columns have weight 2: the reference's shortcut arithmetic stays on the parity kernel"; return p; }
@@ -907,17 +1200,19 @@ FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int sm
         if (g.cp[i + 1] == g.cp[i]) return p;                           // sweep R starts a bit's product at its first edge
     const int zp = (g.Z + 31) & ~31;
     int tcols = 32;
-    while (tcols < (iasp ? 1 : 2) * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;        // fp64 messages take two columns, 12-bit ones one
+    const char* m32 = getenv("LDPCB200_BPSP_MSG32");
+    const bool msg32 = bpsp && m32 && *m32 == '1';                                   // BP_DEC / SP_DEC, opt-in: messages rounded to fp32 (see bpsp_msg)
+    while (tcols < ((iasp || msg32) ? 1 : 2) * g.E * ((zp / 32 + 3) / 4)) tcols *= 2;   // fp64 messages take two columns, 12-bit and fp32 ones one
     if (tcols > 512) { p.note = "the lambda messages (2 columns per edge) do not fit tensor memory"; return p; }
     const size_t smem = (iasp ? sizeof(unsigned) * 3 * (size_t)g.N : sizeof(double) * ((size_t)g.N * (asp ? 3 : ms ? 2 : 1) + 96))
-                        + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16;
+                        + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16 + (bpsp ? ((size_t)g.N + 15) / 16 * 16 : 0);
     if (smem > (size_t)smem_per_block) return p;
     int m = 512 / tcols;
     m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));
     m = std::min(m, 2048 / zp);
-    m = std::min(m, 65536 / (zp * (iasp ? (zp <= 512 ? 128 : 64) : zp <= 256 ? 255 : zp <= 512 ? 128 : 64)));     // register budget of the instance (launch_tasp_fast)
+    m = std::min(m, 65536 / (zp * (iasp ? (zp <= 512 ? 128 : 64) : zp <= 256 ? (bpsp ? 192 : 255) : zp <= 512 ? 128 : 64)));     // register budget of the instance (launch_tasp_fast; the BP / SP rows need fewer than 192)
     if (m < 1) m = 1;
-    p.ok = 1; p.variant = 0; p.tmem = 1;
+    p.ok = 1; p.variant = 0; p.tmem = 1; p.msg32 = msg32;
     p.threads = zp; p.frames_per_cta = 1; p.ctas_per_sm = m;
     p.smem_bytes = std::min(lms_tmem_pad_smem(smem, m), (size_t)smem_per_block);
     p.tab.assign(sizeof(TaspTab), 0);
@@ -929,6 +1224,17 @@ FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int sm
 cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s, double alpha)
 {
     const TaspTab& T = *reinterpret_cast<const TaspTab*>(p.tab.data());
+    if (decoder_id == LDPCB200_BP_DEC || decoder_id == LDPCB200_SP_DEC) {
+        void (*kb)(const TaspTab, const QcDev, const FrameIO);
+        const bool sp = decoder_id == LDPCB200_SP_DEC, w1 = p.msg32 != 0;
+#define BPSP_PICK(SPV, WV) (p.threads <= 128 ? bpsp_fast_kernel<128, SPV, WV> : p.threads <= 256 ? bpsp_fast_kernel<256, SPV, WV> : p.threads <= 512 ? bpsp_fast_kernel<512, SPV, WV> : bpsp_fast_kernel<1024, SPV, WV>)
+        kb = sp ? (w1 ? BPSP_PICK(true, 1) : BPSP_PICK(true, 2)) : (w1 ? BPSP_PICK(false, 1) : BPSP_PICK(false, 2));
+#undef BPSP_PICK
+        cudaError_t e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+        if (e != cudaSuccess) return e;
+        kb<<<grid, p.threads, p.smem_bytes, s>>>(T, g, io);
+        return cudaGetLastError();
+    }
     if (decoder_id == LDPCB200_MS_DEC) {
         void (*km)(const TaspTab, const QcDev, const FrameIO, const double) =
             p.threads <= 128 ? ms64_fast_kernel<128> : p.threads <= 256 ? ms64_fast_kernel<256> : p.threads <= 512 ? ms64_fast_kernel<512> : ms64_fast_kernel<1024>;

@@ -162,6 +162,8 @@ class Decoder:
             d["name"] = "ms64_fast_kernel (table-driven, double, messages in tensor memory)"
         if d["fast"] == 1 and self.decoder_id == IASP_DEC:
             d["name"] = "iasp_fast_kernel (table-driven, 12-bit fixed point, messages in tensor memory)"
+        if d["fast"] == 1 and self.decoder_id in (BP_DEC, SP_DEC):
+            d["name"] = "bpsp_fast_kernel<%s> (table-driven, double, messages in tensor memory)" % ("SP" if self.decoder_id == SP_DEC else "BP")
         if d["fast"] == 1 and self.decoder_id == ASP_DEC:
             d["name"] = "asp_fast_kernel (table-driven, double, messages in tensor memory)"
         if "%s" in d["name"]:

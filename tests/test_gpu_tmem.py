@@ -63,6 +63,39 @@ def test_sumprod_fast_equals_parity_kernel(ldpc, po, monkeypatch, dec):
         assert np.array_equal(a["iters"][:60], want["iters"]) and np.array_equal(a["hard"][:60], want["hard"])
 
 
+@pytest.mark.parametrize("dec", ["BP", "SP"])
+def test_bp_sp_fast_kernels_against_the_parity_kernels(ldpc, po, monkeypatch, dec):
+    """bpsp_fast_kernel (tasp_fast.cu): BP_DEC regroups the reference's log-domain expressions into the product form (one exp,
+    one log per edge instead of two each), SP_DEC divides the edge's own message out of the column product -- the float class
+    of the parity bar: identical decisions and iteration counts (here: on every frame), posteriors within 1e-4 relative
+    (here: 1e-7), against the parity kernel (the reference's literal expressions) and the oracle; fixed-iteration mode
+    reports the first success; a single frame; simulate == decode(generate_llr)."""
+    did = getattr(po, dec)
+    for code, Z, snr in [("c4_wifi_12x24", 81, 2.0), ("ref32x16_b", 126, 2.5), ("c4_wifi_12x24", 81, 6.0)]:
+        hd, llr = _llr(code, Z, snr, 300, 35)
+        llr = llr.astype(np.float64)
+        monkeypatch.delenv("LDPCB200_NO_TASP_FAST", raising=False)
+        with ldpc.Decoder(hd, Z, did) as d:
+            assert d.kernel_info()["tmem"], d.kernel_info()
+            a = d.decode(llr, 20, want_post=True)
+            fixed = d.decode(llr, 20, no_early_exit=True)
+            one = d.decode(llr[7:8], 20)
+            sim = d.simulate(snr, 200, 20, seed=4, want_per_frame=True)
+            again = d.decode(d.generate_llr(snr, 200, seed=4, dtype=np.float64), 20)
+        monkeypatch.setenv("LDPCB200_NO_TASP_FAST", "1")
+        with ldpc.Decoder(hd, Z, did) as d:
+            assert d.kernel_info()["fast"] == 0
+            b = d.decode(llr, 20, want_post=True)
+        assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["hard"], b["hard"])
+        rel = np.abs(a["post"] - b["post"]) / np.maximum(np.abs(b["post"]), 1e-300)
+        assert np.max(rel) <= 1e-7, np.max(rel)
+        assert np.array_equal(fixed["iters"], a["iters"]) and np.array_equal(one["iters"], a["iters"][7:8])
+        want = po.orc_decode(did, hd, Z, llr[:80], 20)
+        assert np.array_equal(a["iters"][:80], want["iters"]) and np.array_equal(a["hard"][:80], want["hard"])
+        assert np.array_equal(sim["per_frame"] >> 31, (again["hard"].sum(axis=1) > 0).astype(np.uint32))
+        assert sim["iter_sum"] == int(np.abs(again["iters"]).sum())
+
+
 def test_tmem_lms_long_run_against_oracle(ldpc, po):
     """6 000 frames at the waterfall: any ordering bug between the lanes of a layer shows up as a handful of frames."""
     hd, llr = _llr("ref32x16_b", 256, 2.2, 6000, 35)

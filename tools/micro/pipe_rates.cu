@@ -8,10 +8,11 @@
 template <int OP>
 __global__ void __launch_bounds__(1024) rate(unsigned* out, unsigned a0, unsigned b0)
 {
-    unsigned r[8];
+    __align__(8) unsigned r[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = a0 + threadIdx.x * 8 + i;
     unsigned b = b0 + threadIdx.x, c = b0 * 3 + 1;
+    double db = 1.0 + 1e-9 * b0, dc = 1e-9 * threadIdx.x;
 #pragma unroll 1
     for (int it = 0; it < ITERS / 4; it++) {
 #pragma unroll
@@ -35,6 +36,9 @@ __global__ void __launch_bounds__(1024) rate(unsigned* out, unsigned a0, unsigne
             if (OP == 13) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
             if (OP == 14) asm volatile("fma.rn.relu.f16x2 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));
             if (OP == 15) asm volatile("add.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));
+            if (OP == 16) { double* dp = (double*)&r[i & ~1]; if ((i & 1) == 0) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(*dp) : "d"(db), "d"(dc)); }
+            if (OP == 17) { double* dp = (double*)&r[i & ~1]; if ((i & 1) == 0) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(*dp) : "d"(db)); }
+            if (OP == 18) { double* dp = (double*)&r[i & ~1]; if ((i & 1) == 0) asm volatile("rcp.approx.ftz.f64 %0, %0;" : "+d"(*dp)); }
         }
       }
     }
@@ -60,7 +64,7 @@ static void run(const char* name, int sms, double ghz)
     cudaEventElapsedTime(&ms, e0, e1);
     // SASS instructions per source statement (cuobjdump of this file): ptxas fuses two dependent two-input minima / adds into
     // one three-input instruction (VHMNMX, VIMNMX3, FMNMX3, IADD3)
-    const double mult = (OP == 0 || OP == 13 || OP == 11 || OP == 3 || OP == 10 || OP == 5 || OP == 15) ? 0.5 : 1.0;
+    const double mult = (OP >= 16) ? 0.5 : (OP == 0 || OP == 13 || OP == 11 || OP == 3 || OP == 10 || OP == 5 || OP == 15) ? 0.5 : 1.0;
     const double winst = 32.0 * ITERS * 8 * mult;                          // per SM: 32 warps
     printf("{\"op\": \"%s\", \"ms\": %.4f, \"warp_inst_per_clk_per_sm\": %.3f}\n", name, ms, winst / (ms * 1e-3 * ghz * 1e9));
     cudaFree(d);
@@ -91,5 +95,8 @@ int main()
     run<8>("fma.rn.f32 (FFMA)", sms, ghz);
     run<12>("add.rn.f32 (FADD)", sms, ghz);
     run<15>("add.u32 (pairs fused to IADD3)", sms, ghz);
+    run<16>("fma.rn.f64 (DFMA)", sms, ghz);
+    run<17>("add.rn.f64 (DADD)", sms, ghz);
+    run<18>("rcp.approx.ftz.f64 (MUFU.RCP64H)", sms, ghz);
     return 0;
 }
