@@ -16,6 +16,8 @@
  *       direct_inverse_perm.cpp:139, :312, :785               ldpcb200_set_interleaver
  *   bp_simulation's frame loop         bp_simulation.cpp:591-824
  *       (noise -> LLR -> puncture -> decode -> count)         ldpcb200_simulate
+ *   the search caller's loop over candidate codes             ldpcb200_simulate_codes
+ *       main_good_code_search.cpp:267-411
  *
  * Conventions kept from the reference: LLR = log P(0)/P(1), positive => bit 0
  * (bp_simulation.cpp:603); a frame is N = c*Z values, block column i at [i*Z, (i+1)*Z), parity
@@ -157,6 +159,17 @@ int ldpcb200_decode_batch(ldpcb200_handle h, const void* llr, int llr_dtype, int
  * (bp_simulation.cpp:591, 820) in exact frame order. */
 int ldpcb200_simulate(ldpcb200_handle h, const ldpcb200_sim_params* sp,
                       ldpcb200_counters* out, uint32_t* per_frame);
+
+/* The same round for MANY candidate codes in one launch -- what the code-search caller does with every candidate it
+ * generates (main_good_code_search.cpp:267-411: generate_code, then bp_simulation at one SNR, :320-338).  hds: n_codes
+ * matrices of the handle's shape (b x c, same lifting, the same number of circulants E; the masks may differ), row-major one
+ * after the other.  The handle (TASP_DEC, the decoder files/input32_16.jsonx names) is only the launch plan: its own matrix
+ * does not take part, and it is kept across calls.  out: n_codes counter blocks; per_frame (optional, host): n_codes x
+ * n_frames records as in ldpcb200_simulate.  Every code sees the same noise (frames first_frame .. of stream sp->stream):
+ * common random numbers, as the reference's reset_random() before each candidate (:316) gives it.
+ * LDPCB200_EUNSUPPORTED if the handle is not a TASP_DEC handle on the tensor-memory kernel or a matrix does not fit it. */
+int ldpcb200_simulate_codes(ldpcb200_handle h, int n_codes, const int16_t* hds, const ldpcb200_sim_params* sp,
+                            ldpcb200_counters* out, uint32_t* per_frame);
 
 /* The channel LLRs ldpcb200_simulate would feed the decoder, written out (host, F32 or F64) so the
  * identical buffer can be given to the reference. */

@@ -528,6 +528,90 @@ int ldpcb200_simulate(ldpcb200_handle h, const ldpcb200_sim_params* sp, ldpcb200
     return 0;
 }
 
+int ldpcb200_simulate_codes(ldpcb200_handle h, int n_codes, const int16_t* hds, const ldpcb200_sim_params* sp,
+                            ldpcb200_counters* out, uint32_t* per_frame)
+{
+    int rc = check_sim(h, sp);
+    if (rc) return rc;
+    if (n_codes < 0 || (n_codes > 0 && (!hds || !out))) return fail(LDPCB200_EINVAL, "bad argument");
+    if (n_codes == 0) return 0;
+    if (n_codes > 65535) return fail(LDPCB200_EINVAL, "at most 65535 codes per call (the grid's second dimension)");
+    memset(out, 0, sizeof(*out) * (size_t)n_codes);
+    if (sp->n_frames == 0) return 0;
+    if (sp->n_frames > 0x7fffffffu) return fail(LDPCB200_EINVAL, "n_frames too large for one round");
+    if (sp->flags & LDPCB200_OUT_ON_DEVICE) return fail(LDPCB200_EINVAL, "per_frame must be a host buffer here");
+    if (h->decoder_id != LDPCB200_TASP_DEC || !h->fast.ok)
+        return fail(LDPCB200_EUNSUPPORTED, "simulate_codes needs a TASP_DEC handle on the tensor-memory kernel (use_fast >= 1, messages fitting tensor memory)");
+    DeviceGuard guard(h->device);
+    const QcHost& g0 = h->g;
+    const int b = g0.b, c = g0.c, Z = g0.Z;
+    // tables of all codes in one blob: per code rp (b + 1) | col (E) | sh (E), each padded to 4 ints
+    auto pad4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
+    const size_t per_code = pad4(b + 1) + 2 * pad4(g0.E);
+    std::vector<int> blob(per_code * (size_t)n_codes, 0);
+    for (int k = 0; k < n_codes; k++) {
+        QcHost g;
+        if (!g.build(hds + (size_t)k * b * c, b, c, Z)) return fail(LDPCB200_EINVAL, "code %d: bad base matrix", k);
+        if (g.E != g0.E) return fail(LDPCB200_EUNSUPPORTED, "code %d has %d circulants, the handle's shape has %d", k, g.E, g0.E);
+        if (g.maxdeg > LDPCB200_MAX_ROW_WEIGHT || g.maxdeg > 20 || g.mindeg < 2) return fail(LDPCB200_EUNSUPPORTED, "code %d: row weights must be 2 .. 20", k);
+        int* base = blob.data() + per_code * (size_t)k;
+        std::copy(g.rp.begin(), g.rp.end(), base);
+        std::copy(g.col.begin(), g.col.end(), base + pad4(b + 1));
+        std::copy(g.sh.begin(), g.sh.end(), base + pad4(b + 1) + pad4(g0.E));
+    }
+    const size_t nf = sp->n_frames;
+    DevBuf d_blob, d_gs, d_ios, d_cnt, d_pf;
+    struct Free { DevBuf *a, *b, *c, *d, *e; ~Free() { a->release(); b->release(); c->release(); d->release(); e->release(); } } fr{&d_blob, &d_gs, &d_ios, &d_cnt, &d_pf};
+    CU(d_blob.reserve(blob.size() * sizeof(int)));
+    CU(d_gs.reserve(sizeof(QcDev) * (size_t)n_codes));
+    CU(d_ios.reserve(sizeof(FrameIO) * (size_t)n_codes));
+    CU(d_cnt.reserve(sizeof(unsigned long long) * 8 * (size_t)n_codes));              // per code: 6 counters | frame ticket | pad
+    if (per_frame) CU(d_pf.reserve(sizeof(uint32_t) * nf * (size_t)n_codes));
+    CU(cudaMemcpyAsync(d_blob.p, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long) * 8 * (size_t)n_codes, h->stream));
+    std::vector<QcDev> gs((size_t)n_codes);
+    std::vector<FrameIO> ios((size_t)n_codes);
+    FrameIO io;
+    memset(&io, 0, sizeof io);
+    io.nf = (int)nf; io.maxiter = sp->max_iterations; io.flags = sp->flags & LDPCB200_NO_EARLY_EXIT;
+    io.llr_dtype = LDPCB200_F32; io.post_dtype = LDPCB200_F64;
+    fill_channel(h, sp, io.ch);
+    for (int k = 0; k < n_codes; k++) {
+        const int* base = (const int*)d_blob.p + per_code * (size_t)k;
+        QcDev d = h->gd;                                                               // geometry of the shape; the edge lists of code k
+        d.rp = base; d.col = base + pad4(b + 1); d.sh = base + pad4(b + 1) + pad4(g0.E);
+        d.row = nullptr; d.cp = nullptr; d.cedge = nullptr; d.pk = nullptr;            // (the TASP kernel reads rp, col, sh only)
+        gs[(size_t)k] = d;
+        FrameIO x = io;
+        unsigned long long* cnt = (unsigned long long*)d_cnt.p + 8 * (size_t)k;
+        x.counters = cnt;
+        x.next_frame = (unsigned int*)(cnt + 6);
+        x.per_frame = per_frame ? (uint32_t*)d_pf.p + nf * (size_t)k : nullptr;
+        ios[(size_t)k] = x;
+    }
+    CU(cudaMemcpyAsync(d_gs.p, gs.data(), sizeof(QcDev) * (size_t)n_codes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_ios.p, ios.data(), sizeof(FrameIO) * (size_t)n_codes, cudaMemcpyHostToDevice, h->stream));
+    // CTAs per code: enough to fill the SMs over all codes, never more than frames
+    int grid_x = (h->num_sms * h->fast.ctas_per_sm + n_codes - 1) / n_codes;
+    grid_x = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid_x, nf));
+    h->last_launches = 0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(launch_tasp_multi(h->fast, (const QcDev*)d_gs.p, (const FrameIO*)d_ios.p, n_codes, grid_x, h->stream));
+    h->last_launches++;
+    CU(cudaEventRecord(h->ev1, h->stream));
+    std::vector<unsigned long long> cnt(8 * (size_t)n_codes);
+    CU(cudaMemcpyAsync(cnt.data(), d_cnt.p, sizeof(unsigned long long) * cnt.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (per_frame) CU(cudaMemcpyAsync(per_frame, d_pf.p, sizeof(uint32_t) * nf * (size_t)n_codes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    for (int k = 0; k < n_codes; k++) {
+        const unsigned long long* x = cnt.data() + 8 * (size_t)k;
+        out[k].frames = x[0]; out[k].frame_errors = x[1]; out[k].info_bit_errors = x[2]; out[k].undetected = x[3];
+        out[k].iter_sum = x[4]; out[k].bit_errors = x[5];
+    }
+    return 0;
+}
+
 int ldpcb200_generate_llr(ldpcb200_handle h, const ldpcb200_sim_params* sp, void* llr, int llr_dtype)
 {
     int rc = check_sim(h, sp);

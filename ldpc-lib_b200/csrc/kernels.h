@@ -45,6 +45,8 @@ cudaError_t launch_ms_fast(const FastPlan& p, const DecParams& dp, const FrameIO
 // TASP_DEC / ASP_DEC in double with the messages in tensor memory (tasp_fast.cu); table-driven, any code that fits
 FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block);
 cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s, double alpha = 0.0);
+// TASP_DEC on n_codes matrices of the handle's shape in one launch: grid (grid_x, n_codes), d_gs / d_ios device arrays
+cudaError_t launch_tasp_multi(const FastPlan& p, const QcDev* d_gs, const FrameIO* d_ios, int n_codes, int grid_x, cudaStream_t s);
 
 // ---- utilities (channel.cu)
 // packed words -> one byte per bit

@@ -277,8 +277,8 @@ __device__ __forceinline__ int tf_syndrome(const double* gam, const unsigned* et
 }
 
 // FL: 0 TASP_DEC, 1 LCHE_DEC, 2 LMS_DEC in double
-template <int MAXT, int FL>
-__global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
+template <int FL>
+__device__ __forceinline__ void tasp_fast_body(const TaspTab& T, const QcDev& g, const FrameIO& io)
 {
     extern __shared__ __align__(16) double tf_smem[];
     const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
@@ -344,6 +344,25 @@ __global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((unsigned)T.tcols) : "memory");
     }
+}
+
+template <int MAXT, int FL>
+__global__ void __launch_bounds__(MAXT, 1) tasp_fast_kernel(const TaspTab T, const QcDev g, const FrameIO io)
+{
+    tasp_fast_body<FL>(T, g, io);
+}
+
+// Many candidate codes of one shape in ONE launch (the code-search caller, main_good_code_search.cpp:
+// 267-411, scores every candidate with the same short TASP_DEC simulation): blockIdx.y is the code.  Each code has its own
+// edge tables, frame counter, error counters and (optional) per-frame records -- gs[k] / ios[k], device arrays -- and the
+// codes share the geometry T (b, c, Z, E: same shape, same number of circulants) and the kernel; the table-driven kernel
+// needs no compilation step, which is what makes a fresh matrix per grid row possible.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) tasp_multi_kernel(const TaspTab T, const QcDev* __restrict__ gs, const FrameIO* __restrict__ ios)
+{
+    const QcDev g = gs[blockIdx.y];
+    const FrameIO io = ios[blockIdx.y];
+    tasp_fast_body<0>(T, g, io);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1219,6 +1238,17 @@ FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int sm
     TaspTab& T = *reinterpret_cast<TaspTab*>(p.tab.data());
     T.b = g.b; T.c = g.c; T.Z = g.Z; T.N = g.N; T.R = g.R; T.E = g.E; T.nwords = (g.N + 31) / 32; T.tcols = tcols;
     return p;
+}
+
+cudaError_t launch_tasp_multi(const FastPlan& p, const QcDev* d_gs, const FrameIO* d_ios, int n_codes, int grid_x, cudaStream_t s)
+{
+    const TaspTab& T = *reinterpret_cast<const TaspTab*>(p.tab.data());
+    void (*kern)(const TaspTab, const QcDev*, const FrameIO*) =
+        p.threads <= 128 ? tasp_multi_kernel<128> : p.threads <= 256 ? tasp_multi_kernel<256> : p.threads <= 512 ? tasp_multi_kernel<512> : tasp_multi_kernel<1024>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(grid_x, n_codes), p.threads, p.smem_bytes, s>>>(T, d_gs, d_ios);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s, double alpha)

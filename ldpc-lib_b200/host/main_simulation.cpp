@@ -87,7 +87,11 @@ int main_simulation(int argc, char* argv[])
         matrix<int> org_HM, coef;
 
         rec.select("_SNRs").cast_to(snrs);
-        rec.select("_q_mod").cast_to(q_mod);
+        // The reference's `search` writes its result records WITHOUT `_q_mod` (main_good_code_search.cpp:383-399), so its
+        // own `simulation` rejects them until the field is added by hand; the engine is binary only, so a
+        // missing field means 2 and search -> simulation round-trips.
+        if (rec.can_select("_q_mod")) rec.select("_q_mod").cast_to(q_mod);
+        else q_mod = 2;
         rec.select("_decoder_type").cast_to(decoder_type);
         if (q_mod > 2) die("code #%d: _q_mod = %d: GF(q) codes are outside the B200 engine", code_idx, q_mod);
         rec.select("_lifting").cast_to(tailbite_length);

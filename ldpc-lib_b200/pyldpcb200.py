@@ -81,6 +81,7 @@ def lib():
         L.ldpcb200_girth_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ldpcb200_interleaver_tables.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]
         L.ldpcb200_set_interleaver.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ldpcb200_simulate_codes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SimParams), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -239,6 +240,23 @@ class Decoder:
         sp = self._sim(snr_db, n_frames, 0, modulation, punct, seed, stream, first_frame, flags, qam_T)
         _check(lib().ldpcb200_generate_llr(self._h, C.byref(sp), _ptr(out), dt))
         return out
+
+    def simulate_codes(self, hds, snr_db, n_frames, maxiter, modulation=MOD_BPSK, punct=0, seed=1, stream=0, first_frame=0,
+                       no_early_exit=False, want_per_frame=False):
+        """One simulate() round for many candidate matrices of this handle's shape in ONE launch (TASP_DEC; the search
+        caller's loop, main_good_code_search.cpp:267-411).  hds: [K, b, c] -> list of K counter dicts."""
+        hds = np.ascontiguousarray(hds, dtype=np.int16)
+        assert hds.ndim == 3 and hds.shape[1:] == (self.b, self.c), hds.shape
+        K = hds.shape[0]
+        sp = self._sim(snr_db, n_frames, maxiter, modulation, punct, seed, stream, first_frame, NO_EARLY_EXIT if no_early_exit else 0, 26.0)
+        out = (Counters * K)()
+        pf = np.zeros((K, n_frames), np.uint32) if want_per_frame else None
+        _check(lib().ldpcb200_simulate_codes(self._h, K, _ptr(hds), C.byref(sp), out, _ptr(pf)))
+        res = [o.as_dict() for o in out]
+        if want_per_frame:
+            for k, d in enumerate(res):
+                d["per_frame"] = pf[k]
+        return res
 
     def set_interleaver(self, direct=None, inverse=None):
         """Attach (or with no arguments remove) a bit interleaver: simulate() / generate_llr() then feed decoder input i with the

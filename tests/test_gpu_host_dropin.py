@@ -140,6 +140,21 @@ def test_main_simulation_interleaver_modes(tmp_path):
         assert all(0.0 < f <= 1.0 for f in outs[key][0]), (key, outs[key][0])
 
 
+def test_search_output_without_q_mod_is_accepted(tmp_path):
+    """The reference's `search` leaves `_q_mod` out of the records it writes (main_good_code_search.cpp:383-399) and its
+    `simulation` then refuses them; the drop-in driver reads a missing field as 2 (binary), so search -> simulation round-trips."""
+    base = open(os.path.join(ROOT, "configs", "sim_c1_lms.jsonx")).read().replace("error_blocks = 100", "error_blocks = 10")
+    codes = open(os.path.join(ROOT, "configs", "sim_c1_lms_codes.jsonx")).read()
+    assert "_q_mod" in codes
+    (tmp_path / "sim_c1_lms_codes.jsonx").write_text(re.sub(r"^\s*_q_mod\s*=.*\n", "", codes, flags=re.M))
+    cfg = tmp_path / "in.jsonx"
+    cfg.write_text(base)
+    out = tmp_path / "out.jsonx"
+    r = subprocess.run([os.path.join(PKG, "bin", "main"), "simulation", str(cfg), str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert len(parse_result(out)[0]) == 3
+
+
 @pytest.mark.parametrize("Q", [16, 64, 256])
 def test_demodulate_function_boundary(ldpc, Q):
     """Demodulate() with m = log2(Q), LLR and P1 outputs, against the reference's recorded outputs: only exp/log may
