@@ -17,9 +17,9 @@
 // QAM-16/64/256 use the intended channel r = s + sigmaQAM n with Demodulate(m = log2 Q); the reference's
 // own wiring of that path is broken.
 //
-// Out of scope here and refused loudly: GF(q) codes (q_mod > 2) and bit interleavers other than the
-// identity for QAM-16/64/256 (with one bit per channel use every interleaver is statistically the identity) --
-// SURVEY.md §8f "next".
+// Bit interleavers (permutation_type 1-4, direct_inverse_perm.cpp) are applied on the device: the index tables are
+// built once per call (ldpcb200_interleaver_tables) and the decoder's first load gathers through them.
+// Out of scope here and refused loudly: GF(q) codes (q_mod > 2) -- SURVEY.md §8f "next".
 #include "bp_simulation.h"
 
 #include <algorithm>
@@ -112,7 +112,9 @@ std::pair<double, double> bp_simulation(
             p.device = devs[k];
             int rc = ldpcb200_create(hd.data(), b, c, M, decoder_type, &p, &h);
             if (rc) {
-                if (de && std::string(de) == "all" && !eng.empty()) break;
+                // "all" asks for ordinals until the engine says there is no such device; any other failure is an error
+                const bool past_the_last = rc == LDPCB200_EINVAL && strstr(ldpcb200_last_error(), "out of range") != NULL;
+                if (de && std::string(de) == "all" && !eng.empty() && past_the_last) break;
                 die("bp_simulation: cannot open the decoder on device %d: %s", devs[k], ldpcb200_last_error());
             }
             eng.push_back(h);
@@ -153,6 +155,7 @@ std::pair<double, double> bp_simulation(
     std::vector<std::vector<uint32_t>> rec(G);
     std::vector<int> rcs(G);
     std::vector<float> ms(G);
+    std::vector<std::string> errs(G);                           // ldpcb200_last_error() is per thread: taken inside the worker
     while (!stop && nde < n_frame_errors && experiment < limit) {
         const long long want = std::min<long long>(limit - experiment, per_gpu * G);
         // GPU g decodes frames [base + off[g], base + off[g] + cnt[g]) of the stream
@@ -171,6 +174,7 @@ std::pair<double, double> bp_simulation(
             ldpcb200_counters co;
             rcs[g] = ldpcb200_simulate(eng[g], &sp, &co, rec[g].data());
             if (!rcs[g]) ldpcb200_last_kernel_ms(eng[g], &ms[g], NULL);
+            else errs[g] = ldpcb200_last_error();
         };
         if (G == 1) run(0);
         else {
@@ -179,7 +183,7 @@ std::pair<double, double> bp_simulation(
             for (auto& t : th) t.join();
         }
         for (int g = 0; g < G; g++)
-            if (rcs[g]) die("bp_simulation: simulate failed on GPU %d (error %d)", g, rcs[g]);
+            if (rcs[g]) die("bp_simulation: simulate failed on GPU %d (error %d): %s", g, rcs[g], errs[g].c_str());
         gpu_ms += *std::max_element(ms.begin(), ms.end());
         decoded += want;
         // the reference's loop body after the decoder call, frame by frame (:731-743, 805-823)

@@ -140,6 +140,29 @@ def test_main_simulation_interleaver_modes(tmp_path):
         assert all(0.0 < f <= 1.0 for f in outs[key][0]), (key, outs[key][0])
 
 
+def test_one_process_all_gpus_gives_the_single_gpu_result(tmp_path):
+    """LDPCB200_DEVICES=all: one handle and one host thread per GPU inside one process (host/bp_simulation.cpp); frames are a
+    pure function of (seed, frame index) and the stop rules run in frame order, so the result file is the single-GPU one."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    base = open(os.path.join(ROOT, "configs", "sim_c1_lms.jsonx")).read().replace("error_blocks = 100", "error_blocks = 30")
+    (tmp_path / "sim_c1_lms_codes.jsonx").write_text(open(os.path.join(ROOT, "configs", "sim_c1_lms_codes.jsonx")).read())
+    cfg = tmp_path / "in.jsonx"
+    cfg.write_text(base)
+    res = {}
+    for devs in ("", "all", "0,1"):
+        out = tmp_path / ("out_%s.jsonx" % (devs.replace(",", "_") or "one"))
+        env = dict(os.environ)
+        env.pop("LDPCB200_DEVICES", None)
+        if devs:
+            env["LDPCB200_DEVICES"] = devs
+        r = subprocess.run([os.path.join(PKG, "bin", "main"), "simulation", str(cfg), str(out)], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0, (devs, r.stderr)
+        res[devs] = parse_result(out)[:2]
+    assert res["all"] == res[""] and res["0,1"] == res[""]
+
+
 def test_search_output_without_q_mod_is_accepted(tmp_path):
     """The reference's `search` leaves `_q_mod` out of the records it writes (main_good_code_search.cpp:383-399) and its
     `simulation` then refuses them; the drop-in driver reads a missing field as 2 (binary), so search -> simulation round-trips."""

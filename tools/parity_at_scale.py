@@ -2,7 +2,7 @@
 """Parity at scale: the GPU decoders against the COMPILED REFERENCE (oracle/_ref, all host cores) on identical LLR buffers,
 with the frame counts the north-star bars are stated for -- fixed-point bit-exact on >= 10^5 frames, float decoders
 >= 99.99 % frames with identical decisions and iteration counts, posteriors within 1e-4.  Writes one JSON document:
-    python tools/parity_at_scale.py > profiles/r01_parity_at_scale.json
+    python tools/parity_at_scale.py [CASE SUBSTRING] > profiles/r02_parity_at_scale.json
 The reference side is the checker here, never the thing shipped (falls back to the C oracle port when oracle/_ref is absent)."""
 import json
 import multiprocessing as mp
@@ -29,6 +29,8 @@ CASES = [
     ("C1 ASP_DEC double", "ref32x16_b", 126, "ASP", 64, 50, 2.0, 50000),
     ("C4 LMS_DEC fp32 vs reference double", "c4_wifi_12x24", 81, "LMS", 32, 20, 2.0, 200000),
     ("C4 LCHE_DEC double", "c4_wifi_12x24", 81, "LCHE", 64, 20, 2.0, 50000),
+    ("C4 BP_DEC double (product form)", "c4_wifi_12x24", 81, "BP", 64, 20, 2.0, 100000),
+    ("C4 SP_DEC double (own message divided out)", "c4_wifi_12x24", 81, "SP", 64, 20, 2.0, 100000),
 ]
 
 
