@@ -209,6 +209,19 @@ int ldpcb200_interleaver_tables(const int16_t* hd, int b, int c, int Z, int modu
  * permutations (checked); both NULL removes the interleaver. */
 int ldpcb200_set_interleaver(ldpcb200_handle h, const int32_t* direct, const int32_t* inverse);
 
+/* The transmitted codeword of ldpcb200_simulate / ldpcb200_generate_llr: N bytes 0 / 1 in codeword order (host), NULL or
+ * all-zero = the all-zero codeword the reference's loop sends (bp_simulation.cpp:567).  With a real codeword (host/encoder.cpp
+ * qc_encode / random_codeword make them, bp_simulation.cpp:22-192) the bits go through the direct permutation (:573), the Gray
+ * map of QAM_modulator (QAM_modulator.cpp:127-194) or the BPSK map (:600-612), the channel, Demodulate, the inverse
+ * permutation and the puncturing; errors are counted against the codeword (:731-743).  The round then runs as three launches
+ * (LLRs into a device buffer, decode, compare) instead of the fused one. */
+int ldpcb200_set_codeword(ldpcb200_handle h, const uint8_t* bits);
+
+/* The generator's unit-variance noise samples 0 .. n_samples-1 of frames first_frame .. first_frame + n_frames - 1 (host, fp32,
+ * frame-major): sample t is the one added to transmitted position t (BPSK / QAM-4) or to PAM component t = 2 symbol +
+ * component (QAM-16/64/256).  For tests that rebuild the channel with the reference's own modulator and demodulator. */
+int ldpcb200_generate_noise(ldpcb200_handle h, const ldpcb200_sim_params* sp, int n_samples, float* out);
+
 /* Diagnostic: generate and compile (NVRTC, no device needed) the code-specialised LMS_DEC kernel for a matrix
  * and target architecture sm_<major><minor>; *cubin_bytes = size of the result. */
 int ldpcb200_jit_check(const int16_t* hd, int b, int c, int Z, int sm_major, int sm_minor, int* cubin_bytes);

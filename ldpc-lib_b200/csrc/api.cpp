@@ -94,7 +94,8 @@ struct ldpcb200_handle_s {
     int device = 0, num_sms = 0, smem_per_sm = 0, smem_per_block = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf tables, ws, counters, next, bpsynd, coef, perm;
+    DevBuf tables, ws, counters, next, bpsynd, coef, perm, cw, cw_words;
+    bool has_cw = false;                    // cw: the transmitted codeword, one byte per bit; cw_words: packed (ldpcb200_set_codeword)
     bool has_perm = false;                  // perm holds direct[N] | inverse[N] (ldpcb200_set_interleaver)
     size_t ws_stride = 0, smem_ws = 0;      // smem_ws != 0: the table-driven kernel keeps its state in shared memory
     int grid = 0, nt = 0;
@@ -205,6 +206,7 @@ void fill_channel(const ldpcb200_handle_s* h, const ldpcb200_sim_params* sp, Cha
     ch.stream = sp->stream;
     ch.first_frame = sp->first_frame;
     if (h->has_perm) { ch.perm_dir = (const int*)h->perm.p; ch.perm_inv = (const int*)h->perm.p + g.N; }
+    if (h->has_cw) ch.cw = (const unsigned char*)h->cw.p;
 }
 
 int check_sim(const ldpcb200_handle_s* h, const ldpcb200_sim_params* sp)
@@ -346,7 +348,7 @@ int ldpcb200_destroy(ldpcb200_handle h)
         if (s.ev_k) cudaEventDestroy(s.ev_k);
         if (s.ev_out) cudaEventDestroy(s.ev_out);
     }
-    h->tables.release(); h->ws.release(); h->counters.release(); h->next.release(); h->bpsynd.release(); h->coef.release(); h->perm.release();
+    h->tables.release(); h->ws.release(); h->counters.release(); h->next.release(); h->bpsynd.release(); h->coef.release(); h->perm.release(); h->cw.release(); h->cw_words.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -515,8 +517,34 @@ int ldpcb200_simulate(ldpcb200_handle h, const ldpcb200_sim_params* sp, ldpcb200
     }
     CU(cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev0, h->stream));
-    rc = launch_decoder(h, io);
-    if (rc) return rc;
+    if (h->has_cw) {
+        // A transmitted codeword other than all-zero: the fused first loads and error counters of the decode kernels are
+        // for the all-zero one, so the round is three launches per chunk -- LLRs of the codeword through the channel (per-bit
+        // path, interleaver included), decode from that buffer into packed decisions, decisions against the codeword.
+        const int N = h->g.N, nwords = h->gd.nwords;
+        const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)io.nf, ((size_t)512 << 20) / ((size_t)N * 4)));
+        CU(s.llr.reserve((size_t)chunk * N * 4));
+        CU(s.words.reserve((size_t)chunk * nwords * 4));
+        CU(s.iters.reserve((size_t)chunk * 4));
+        for (int f0 = 0; f0 < io.nf; f0 += chunk) {
+            const int nf = std::min(chunk, io.nf - f0);
+            ChannelParams ch = io.ch;
+            ch.first_frame = io.ch.first_frame + (unsigned long long)f0;
+            CU(launch_generate_llr(ch, N, nf, s.llr.p, LDPCB200_F32, h->stream));
+            FrameIO d;
+            memset(&d, 0, sizeof d);
+            d.llr = s.llr.p; d.llr_dtype = LDPCB200_F32; d.nf = nf; d.maxiter = io.maxiter; d.flags = io.flags;
+            d.post_dtype = io.post_dtype; d.hard_words = (uint32_t*)s.words.p; d.iters = (int32_t*)s.iters.p;
+            rc = launch_decoder(h, d);
+            if (rc) return rc;
+            CU(launch_count_errors((const uint32_t*)s.words.p, (const uint32_t*)h->cw_words.p, (const int*)s.iters.p, nf, N, h->g.R, nwords,
+                                   (unsigned long long*)h->counters.p, io.per_frame ? io.per_frame + f0 : nullptr, h->stream));
+            h->last_launches += 2;
+        }
+    } else {
+        rc = launch_decoder(h, io);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(h->ev1, h->stream));
     unsigned long long c[6];
     CU(cudaMemcpyAsync(c, h->counters.p, sizeof c, cudaMemcpyDeviceToHost, h->stream));
@@ -540,6 +568,7 @@ int ldpcb200_simulate_codes(ldpcb200_handle h, int n_codes, const int16_t* hds, 
     if (sp->n_frames == 0) return 0;
     if (sp->n_frames > 0x7fffffffu) return fail(LDPCB200_EINVAL, "n_frames too large for one round");
     if (sp->flags & LDPCB200_OUT_ON_DEVICE) return fail(LDPCB200_EINVAL, "per_frame must be a host buffer here");
+    if (h->has_cw) return fail(LDPCB200_EUNSUPPORTED, "simulate_codes sends the all-zero codeword (a codeword belongs to one matrix)");
     if (h->decoder_id != LDPCB200_TASP_DEC || !h->fast.ok)
         return fail(LDPCB200_EUNSUPPORTED, "simulate_codes needs a TASP_DEC handle on the tensor-memory kernel (use_fast >= 1, messages fitting tensor memory)");
     DeviceGuard guard(h->device);
@@ -640,6 +669,47 @@ int ldpcb200_generate_llr(ldpcb200_handle h, const ldpcb200_sim_params* sp, void
         CU(cudaMemcpyAsync((char*)llr + (size_t)f0 * N * esz, s.llr.p, (size_t)nf * N * esz, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
     }
+    return 0;
+}
+
+int ldpcb200_set_codeword(ldpcb200_handle h, const uint8_t* bits)
+{
+    if (!h) return fail(LDPCB200_EINVAL, "null handle");
+    if (!bits) { h->has_cw = false; return 0; }
+    const int N = h->g.N, nwords = h->gd.nwords;
+    std::vector<uint32_t> words((size_t)nwords, 0u);
+    bool any = false;
+    for (int i = 0; i < N; i++) {
+        if (bits[i] > 1) return fail(LDPCB200_EINVAL, "codeword bit %d is %d (must be 0 or 1)", i, bits[i]);
+        if (bits[i]) { words[(size_t)(i >> 5)] |= 1u << (i & 31); any = true; }
+    }
+    // (that the word satisfies the parity checks is the caller's business: host/encoder.cpp qc_encode / random_codeword make them)
+    if (!any) { h->has_cw = false; return 0; }                     // all-zero: the fused path
+    DeviceGuard guard(h->device);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(h->cw.reserve((size_t)N));
+    CU(h->cw_words.reserve((size_t)nwords * 4));
+    CU(cudaMemcpy(h->cw.p, bits, (size_t)N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->cw_words.p, words.data(), (size_t)nwords * 4, cudaMemcpyHostToDevice));
+    h->has_cw = true;
+    return 0;
+}
+
+int ldpcb200_generate_noise(ldpcb200_handle h, const ldpcb200_sim_params* sp, int n_samples, float* out)
+{
+    int rc = check_sim(h, sp);
+    if (rc) return rc;
+    if (!out || n_samples <= 0) return fail(LDPCB200_EINVAL, "bad argument");
+    if (sp->n_frames == 0) return 0;
+    DeviceGuard guard(h->device);
+    ChannelParams ch;
+    fill_channel(h, sp, ch);
+    const size_t total = (size_t)sp->n_frames * (size_t)n_samples;
+    Slot& s = h->slot[0];
+    CU(s.llr.reserve(total * 4));
+    CU(launch_generate_noise(ch, n_samples, (int)sp->n_frames, (float*)s.llr.p, h->stream));
+    CU(cudaMemcpyAsync(out, s.llr.p, total * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -46,6 +46,67 @@ cudaError_t launch_generate_llr(const ChannelParams& ch, int N, int nf, void* ll
     return cudaGetLastError();
 }
 
+// Error accounting of decoded frames against a transmitted codeword (bp_simulation.cpp:731-743, 805-810) -- the fused decode
+// kernels count against the all-zero codeword the reference sends; with a real codeword (ldpcb200_set_codeword) the decode
+// writes packed decisions and this kernel compares them: one warp per frame.
+__global__ void count_errors_kernel(const uint32_t* __restrict__ hard_words, const uint32_t* __restrict__ cw_words, const int* __restrict__ iters,
+                                    int nf, int N, int R, int nwords, unsigned long long* counters, uint32_t* per_frame)
+{
+    const int lane = threadIdx.x & 31;
+    for (int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < nf; f += (gridDim.x * blockDim.x) >> 5) {
+        int e = 0, ei = 0;
+        for (int w = lane; w < nwords; w += 32) {
+            uint32_t x = hard_words[(size_t)f * nwords + w] ^ cw_words[w];
+            if (32 * w + 32 > N) x &= (N - 32 * w >= 32) ? 0xffffffffu : ((1u << (N - 32 * w)) - 1u);
+            e += __popc(x);
+            const int lo = R - 32 * w;                                           // bits >= R are information bits (:738)
+            ei += __popc(lo <= 0 ? x : (lo >= 32 ? 0u : (x >> lo) << lo));
+        }
+        for (int o = 16; o > 0; o >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, o); ei += __shfl_xor_sync(0xffffffffu, ei, o); }
+        if (lane == 0) {
+            const int ret = iters[f];
+            if (per_frame) per_frame[f] = (e ? 0x80000000u : 0u) | (ret >= 0 ? 0x40000000u : 0u) | (uint32_t)(ei < 0xFFFFFF ? ei : 0xFFFFFF);
+            atomicAdd(&counters[0], 1ull);
+            atomicAdd(&counters[4], (unsigned long long)(ret < 0 ? -ret : ret));
+            if (e) {
+                atomicAdd(&counters[1], 1ull);
+                atomicAdd(&counters[2], (unsigned long long)ei);
+                atomicAdd(&counters[5], (unsigned long long)e);
+                if (ret >= 0) atomicAdd(&counters[3], 1ull);
+            }
+        }
+    }
+}
+
+cudaError_t launch_count_errors(const uint32_t* hard_words, const uint32_t* cw_words, const int* iters, int nf, int N, int R, int nwords,
+                                unsigned long long* counters, uint32_t* per_frame, cudaStream_t s)
+{
+    int grid = (nf + 7) / 8;
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    count_errors_kernel<<<grid, 256, 0, s>>>(hard_words, cw_words, iters, nf, N, R, nwords, counters, per_frame);
+    return cudaGetLastError();
+}
+
+// the generator's N(0,1) samples 0 .. ns-1 of frames [first_frame, first_frame + nf) (tests: the channel against the reference's modulator / demodulator)
+__global__ void generate_noise_kernel(ChannelParams ch, int ns, int nf, float* __restrict__ out)
+{
+    size_t total = (size_t)nf * ns;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
+        size_t f = x / ns;
+        out[x] = channel_noise(ch, ch.first_frame + f, (unsigned int)(x - f * ns));
+    }
+}
+
+cudaError_t launch_generate_noise(const ChannelParams& ch, int ns, int nf, float* out, cudaStream_t s)
+{
+    size_t total = (size_t)nf * ns;
+    int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    if (grid < 1) grid = 1;
+    generate_noise_kernel<<<grid, 256, 0, s>>>(ch, ns, nf, out);
+    return cudaGetLastError();
+}
+
 // IMS_DEC quantiser pre-pass (decoders.cpp:5472-5479): coef[f] = sqrt(N / sum_i y_i^2) with the sum taken in the
 // reference's order, i = 0 .. N-1, in double.  Floating-point addition is not associative, so the chain of one frame
 // cannot be split -- but frames are independent: one LANE per frame, 32 chains per warp, hundreds of thousands in
@@ -64,7 +125,7 @@ __global__ void __launch_bounds__(128) ims_energy_kernel(FrameIO io, int N, doub
             if (f < io.nf) {
                 const unsigned long long frame = io.ch.first_frame + (unsigned long long)f;
                 int i = 0;
-                if (io.ch.m <= 2 && !io.ch.perm_inv) {                 // one Philox block -> four consecutive LLRs (the same values, a quarter of the work)
+                if (io.ch.m <= 2 && !io.ch.perm_inv && !io.ch.cw) {                 // one Philox block -> four consecutive LLRs (the same values, a quarter of the work)
                     for (; i + 4 <= N; i += 4) {
                         float o[4];
                         int d[4];

@@ -180,17 +180,29 @@ __device__ __forceinline__ void channel_llr4_bpsk(const ChannelParams& ch, unsig
     }
 }
 
-// QAM-16/64/256 LLR of bit i (kept out of line: it is heavy in registers and only used by C3-like runs)
-static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, unsigned long long frame, int i)
+// QAM-16/64/256 LLR of the bit at TRANSMITTED position t (kept out of line: it is heavy in registers and only used by C3-like runs)
+static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, unsigned long long frame, int t)
 {
-    // QAM-16/64/256: bit i lives in symbol i / m; the first m/2 bits ride on I, the rest on Q
+    // position t lives in symbol t / m; the first m/2 bits ride on I, the rest on Q
     const int half = ch.m >> 1;
-    int sym = i / ch.m, r = i - sym * ch.m;
+    int sym = t / ch.m, r = t - sym * ch.m;
     int comp = r >= half;
     int bit = r - comp * half;
     float nz = channel_noise(ch, frame, (unsigned int)(2 * sym + comp));
-    // all-zero bits -> natural index 0 -> gray[0] = 0 -> coordinate -(sqrt(Q) - 1)  (QAM_modulator.cpp:127-140)
-    double x = (double)nz * ch.sigma_d - (double)((1 << half) - 1);
+    // the component's bits, MSB first, as a natural index -> gray[] -> coordinate 2 pos - (sqrt(Q) - 1)  (QAM_modulator.cpp:127-194);
+    // all-zero bits -> index 0 -> gray[0] = 0 -> -(sqrt(Q) - 1)
+    int pos = 0;
+    if (ch.cw) {
+        const int gray[16] = { 0, 1, 3, 2, 7, 6, 4, 5, 15, 14, 12, 13, 8, 9, 11, 10 };
+        int z = 0;
+        const int t0 = sym * ch.m + comp * half;
+        for (int q = 0; q < half; q++) {
+            const int src = ch.perm_dir ? __ldg(ch.perm_dir + t0 + q) : t0 + q;          // codeword bit sent at position t0 + q (direct permutation, :573)
+            z = (z << 1) | (int)(ch.cw[src] & 1);
+        }
+        pos = gray[z];
+    }
+    double x = (double)nz * ch.sigma_d + (double)(2 * pos - ((1 << half) - 1));
     double o[4];
     pam_demod(x, 2.0 * ch.sigma_d * ch.sigma_d, ch.T, ch.m, 0, o);
     return (float)(-o[bit]);
@@ -210,14 +222,19 @@ static __device__ __noinline__ void channel_llr_qam_component(const ChannelParam
     for (int b = 0; b < 4; b++) out[b] = b < half ? (float)(-o[b]) : 0.0f;
 }
 
-// Channel LLR (log P0/P1, the decoder-side sign) of decoder input i of frame f for the all-zero codeword: the value
-// received at transmitted position perm_inv[i] (bp_simulation.cpp:684).
+// Channel LLR (log P0/P1, the decoder-side sign) of decoder input i of frame f: the value received at transmitted
+// position perm_inv[i] (bp_simulation.cpp:684), for the all-zero codeword or ch.cw.
 __device__ __forceinline__ float channel_llr(const ChannelParams& ch, unsigned long long frame, int i)
 {
     if (i >= ch.punct_start) return ch.punct_value;
-    if (ch.perm_inv) i = __ldg(ch.perm_inv + i);
-    if (ch.m <= 2) return bpsk_llr(ch, channel_noise(ch, frame, (unsigned int)i));
-    return channel_llr_qam(ch, frame, i);
+    const int t = ch.perm_inv ? __ldg(ch.perm_inv + i) : i;
+    if (ch.m <= 2) {
+        // -2 (sigma n + 2 c - 1) / sigma^2 (:600-612): c = 0 -> (1 - sigma n) 2 / sigma^2, c = 1 -> (-1 - sigma n) 2 / sigma^2
+        const float n = channel_noise(ch, frame, (unsigned int)t);
+        if (ch.cw && (ch.cw[i] & 1)) return __fmul_rn(__fmaf_rn(-ch.sigma, n, -1.0f), ch.llr_scale);
+        return bpsk_llr(ch, n);
+    }
+    return channel_llr_qam(ch, frame, t);
 }
 #endif
 

@@ -22,6 +22,10 @@ struct ChannelParams {
     // identity: perm_dir[j] = decoder input fed by transmitted position j, perm_inv[i] = transmitted position of input i
     const int* perm_dir;
     const int* perm_inv;
+    // transmitted codeword (bp_simulation.cpp:567-577 sends the all-zero one; SURVEY.md 8f row 2 asks for real ones so that the
+    // Gray map is exercised): N bytes 0 / 1 in CODEWORD order on the device, or null for all-zero.  Only the per-bit path
+    // (channel_llr) knows it: the fused first loads are for the all-zero codeword and the API routes around them.
+    const unsigned char* cw;
 };
 
 // Everything one decode launch reads and writes (all pointers are device pointers).

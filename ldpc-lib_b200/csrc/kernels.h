@@ -53,6 +53,10 @@ cudaError_t launch_tasp_multi(const FastPlan& p, const QcDev* d_gs, const FrameI
 cudaError_t launch_unpack_hard(const uint32_t* words, uint8_t* bytes, int nf, int N, int nwords, cudaStream_t s);
 // channel LLRs for frames [first_frame, first_frame + nf) written as F32 or F64
 cudaError_t launch_generate_llr(const ChannelParams& ch, int N, int nf, void* llr, int llr_dtype, cudaStream_t s);
+// error accounting against a transmitted codeword (packed decisions XOR packed codeword), and the raw noise samples (tests)
+cudaError_t launch_count_errors(const uint32_t* hard_words, const uint32_t* cw_words, const int* iters, int nf, int N, int R, int nwords,
+                                unsigned long long* counters, uint32_t* per_frame, cudaStream_t s);
+cudaError_t launch_generate_noise(const ChannelParams& ch, int ns, int nf, float* out, cudaStream_t s);
 // IMS_DEC quantiser pre-pass: coef[f] = sqrt(N / sum y^2), the sum in the reference's sequential order, one lane per frame
 cudaError_t launch_ims_energy(const FrameIO& io, int N, double* coef, cudaStream_t s);
 // Demodulate / QAM_modulator at the function boundary

@@ -81,6 +81,8 @@ def lib():
         L.ldpcb200_girth_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ldpcb200_interleaver_tables.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]
         L.ldpcb200_set_interleaver.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ldpcb200_set_codeword.argtypes = [C.c_void_p, C.c_void_p]
+        L.ldpcb200_generate_noise.argtypes = [C.c_void_p, C.POINTER(SimParams), C.c_int, C.c_void_p]
         L.ldpcb200_simulate_codes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SimParams), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -257,6 +259,22 @@ class Decoder:
             for k, d in enumerate(res):
                 d["per_frame"] = pf[k]
         return res
+
+    def set_codeword(self, bits=None):
+        """The transmitted codeword of simulate() / generate_llr() (N bits 0 / 1); None = all-zero, as the reference sends."""
+        if bits is None:
+            _check(lib().ldpcb200_set_codeword(self._h, None))
+            return
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        assert b.shape == (self.N,)
+        _check(lib().ldpcb200_set_codeword(self._h, _ptr(b)))
+
+    def generate_noise(self, snr_db, n_frames, n_samples, modulation=MOD_BPSK, punct=0, seed=1, stream=0, first_frame=0):
+        """The unit-variance noise samples the channel adds (fp32 [n_frames, n_samples])."""
+        sp = self._sim(snr_db, n_frames, 0, modulation, punct, seed, stream, first_frame, 0, 26.0)
+        out = np.zeros((n_frames, n_samples), np.float32)
+        _check(lib().ldpcb200_generate_noise(self._h, C.byref(sp), n_samples, _ptr(out)))
+        return out
 
     def set_interleaver(self, direct=None, inverse=None):
         """Attach (or with no arguments remove) a bit interleaver: simulate() / generate_llr() then feed decoder input i with the
