@@ -152,7 +152,9 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
         io.bp_syndrome = (uint8_t*)h->bpsynd.p;
         grid = 1;                                   // frames must follow each other, as in the reference
     }
-    if (h->decoder_id == LDPCB200_IMS_DEC) {                // energy pre-pass: the per-frame quantiser scale
+    const bool ims_own_energy = h->decoder_id == LDPCB200_IMS_DEC && h->fast.ok && h->fast.frames_per_cta >= 2 &&
+                                !(io.post && io.post_dtype != default_post_dtype(h->decoder_id, h->p.precision));   // ims_h2.cuh sums the energy itself
+    if (h->decoder_id == LDPCB200_IMS_DEC && !ims_own_energy) {                // energy pre-pass: the per-frame quantiser scale
         CU(h->coef.reserve(sizeof(double) * (size_t)std::max(io.nf, 1)));
         CU(launch_ims_energy(io, h->g.N, (double*)h->coef.p, h->stream));
         io.coef = (const double*)h->coef.p;

@@ -68,7 +68,7 @@ struct ImsH2 {
     static constexpr int GROUP_WORDS = (Y_OFF + N + 1) & ~1;
     static constexpr int MBAR_OFF = G * GROUP_WORDS;
     static constexpr int MISC_OFF = MBAR_OFF + 2;
-    static constexpr int SMEM_WORDS = MISC_OFF + 16;
+    static constexpr int SMEM_WORDS = MISC_OFF + 16 + 2 * (NT / 32 + 2);     // misc | per-warp energy sums + coef (doubles)
 
     struct Consts { unsigned cap, ncap, cap2, scale, dshift, magic, sone; };
 
@@ -250,24 +250,28 @@ struct ImsH2 {
             for (int i = tid; i < N; i += NT) dst[i] = (float)__ldcs(src + i);
         }
     }
-    // the quantiser of :5481-5500 for one value, in the reference's double arithmetic
-    static __device__ __noinline__ int quantise_exact(double val, double coef, const MsSpecParams& sp)
+    // the quantiser of :5481-5500 for one value, in the reference's double arithmetic.  *near: the value before the floor lies
+    // within 1e-9 of an integer (see the energy note in refill())
+    static __device__ __noinline__ int quantise_exact(double val, double coef, const MsSpecParams& sp, bool* near)
     {
         int sign = 0;
         if (val < 0) { val = -val; sign = 1; }
         val *= coef;
         if (val > sp.thr) val = sp.thr;
-        const int ival = (short)floor(div_normal(val * sp.max_quant, sp.thr) + 0.5);   // the correctly rounded quotient without the slow-path branch (channel.cuh)
+        const double u = div_normal(val * sp.max_quant, sp.thr) + 0.5;   // the correctly rounded quotient without the slow-path branch (channel.cuh)
+        const double fl = floor(u);
+        if (u - fl < 1e-9 || u - fl > 1.0 - 1e-9) *near = true;
+        const int ival = (short)fl;
         return sign ? -ival : ival;
     }
     // The same value from an fp32 estimate whenever that cannot be wrong: t = |y| coef max_quant / thr is at most max_quant
     // (<= 127), the estimate is within 1e-4 of it (a few fp32 roundings), so floor(t + 0.5) is decided unless t + 0.5 lies
     // within 1e-3 of an integer -- one value in 500 -- and only then the double arithmetic runs.  cs = coef max_quant / thr.
-    static __device__ __forceinline__ int quantise(double val, float valf, double coef, float cs, const MsSpecParams& sp)
+    static __device__ __forceinline__ int quantise(double val, float valf, double coef, float cs, const MsSpecParams& sp, bool* near)
     {
         const float u = fminf(fabsf(valf) * cs, (float)sp.max_quant) + 0.5f;
         const float fl = floorf(u), frac = u - fl;
-        if (!(frac >= 1e-3f && frac <= 1.0f - 1e-3f)) return quantise_exact(val, coef, sp);
+        if (!(frac >= 1e-3f && frac <= 1.0f - 1e-3f)) return quantise_exact(val, coef, sp, near);
         const int ival = (int)fl;
         return valf < 0.0f ? -ival : ival;
     }
@@ -340,7 +344,7 @@ struct ImsH2 {
     }
 
     // Put the next frame of the batch into half `h` of group `gs` (the whole CTA calls this, between iterations): fp32 LLRs
-    // staged in the group's posterior area, quantised (:5472-5500, coef from the energy pre-pass of channel.cu) into its half of
+    // staged in the group's posterior area, quantised (:5472-5500) into its half of
     // the channel words, its half of the group's message words cleared (dcs[] = 0, :5463-5502).  -> frame index, or -1 when
     // the batch is exhausted (the slot then keeps its old, bounded contents).
     // Tickets are drawn one refill ahead (thread 0 carries the next one): the atomic issued here is only waited for when
@@ -363,13 +367,37 @@ struct ImsH2 {
         __syncthreads();
         const bool f64 = !io.ch.enabled && io.llr_dtype == 0;                       // doubles are quantised as doubles, not through fp32
         const double* src = f64 ? (const double*)io.llr + (size_t)f * N : nullptr;
-        const double coef = io.coef[f];
-        const float cs = (float)(coef * sp.max_quant / sp.thr);
-        for (int i = tid; i < N; i += NT) {
-            const int q = src ? quantise(src[i], (float)src[i], coef, cs, sp) : quantise((double)stage[i], stage[i], coef, cs, sp);
-            const unsigned hv = h2_pack((float)(q - sp.max_data), 0.0f) & 0xffffu;    // iy - max_data: pass B
-            gy[i] = (gy[i] & keep) | (h ? hv << 16 : hv);
-            if (io.aux) io.aux[(size_t)f * N + i] = (short)q;
+        // Per-frame energy normalisation coef = sqrt(N / sum y_i^2) (:5472-5479).  The reference adds the squares one after the
+        // other in double, and floating-point addition is not associative -- but ANY summation order of N non-negative terms is
+        // within 2 N 2^-53 < 1e-12 (relative) of the sequential one, which moves t = |y| coef max_quant / thr (<= 127) by less
+        // than 1.3e-10.  So: sum in parallel, quantise, and note whether any t + 0.5 came within 1e-9 of an integer.  If none
+        // did (all but one frame in 10^6), every floor() is the reference's whatever the order; otherwise thread 0 adds the
+        // squares in the reference's order and the frame is quantised again.  Exact always, sequential almost never -- and the
+        // energy pre-pass kernel (a second generation of every noise sample) is gone.
+        double* s_red = (double*)(s_misc + 16);
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 0) {
+                double part = 0.0;
+                for (int i = tid; i < N; i += NT) { const double v = src ? src[i] : (double)stage[i]; part += v * v; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if ((tid & 31) == 0) s_red[tid >> 5] = part;
+                __syncthreads();
+                if (tid == 0) { double en = 0.0; for (int w = 0; w < NWARPS; w++) en += s_red[w]; s_red[NWARPS] = sqrt(N / en); }
+            } else {
+                if (tid == 0) { double en = 0.0; for (int i = 0; i < N; i++) { const double v = src ? src[i] : (double)stage[i]; en += v * v; } s_red[NWARPS] = sqrt(N / en); }   // :5472-5479
+            }
+            __syncthreads();
+            const double coef = s_red[NWARPS];
+            const float cs = (float)(coef * sp.max_quant / sp.thr);
+            bool near = false;
+            for (int i = tid; i < N; i += NT) {
+                const int q = src ? quantise(src[i], (float)src[i], coef, cs, sp, &near) : quantise((double)stage[i], stage[i], coef, cs, sp, &near);
+                const unsigned hv = h2_pack((float)(q - sp.max_data), 0.0f) & 0xffffu;    // iy - max_data: pass B
+                gy[i] = (gy[i] & keep) | (h ? hv << 16 : hv);
+                if (io.aux) io.aux[(size_t)f * N + i] = (short)q;
+            }
+            if (pass == 1 || !__syncthreads_or(near)) break;
         }
         tmem_wait_st();
         __syncthreads();

@@ -54,7 +54,8 @@ size_t ims_h2_smem_bytes(int c, int Z, int groups)
 {
     const size_t y_off = 2 * (size_t)c * Z, n = (size_t)c * Z;
     const size_t group = (y_off + n + 1) & ~(size_t)1;
-    return sizeof(float) * (groups * group + 2 + 16);
+    const int zp = (Z + 31) / 32 * 32;
+    return sizeof(float) * (groups * group + 2 + 16 + 2 * (groups * zp / 32 + 2));
 }
 
 size_t lms_tmem_pad_smem(size_t smem, int minb)

@@ -134,3 +134,32 @@ def test_ims_fp16_pairs_other_alpha(ldpc, po):
             assert d.kernel_info()["frames_per_cta"] >= 2
             got = d.decode(llr, 10, want_post=True)
         assert np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["post"], want["post"]), alpha
+
+
+def test_ims_energy_fallback_on_values_at_a_rounding_boundary(ldpc, po):
+    """ims_h2.cuh sums the frame energy in parallel and only falls back to the reference's sequential order when a value lands
+    within 1e-9 of a quantiser boundary.  Frames built to sit ON boundaries (one value solved so that |y| coef max_quant / thr
+    = k + 1/2 to the last bit, where the order of the additions decides the result) must still be the oracle's, value for value."""
+    hd, _ = load_code("ref32x16_a")
+    Z, N = 126, 32 * 126
+    rng = np.random.default_rng(77)
+    frames = []
+    for k in (0, 3, 10, 17, 25, 30):
+        y = rng.normal(1.0, 0.7, N) * rng.choice([-1.0, 1.0], N)
+        j = int(rng.integers(0, N))
+        b = 0.3
+        for _ in range(200):                                        # fixed point of b coef(b) 31 / 1.4 = k + 1/2
+            y[j] = b
+            en = 0.0
+            for v in y:                                             # the reference's order
+                en += v * v
+            b = (k + 0.5) * 1.4 / 31.0 / np.sqrt(N / en)
+        y[j] = b
+        frames.append(y)
+    llr = np.array(frames + [rng.normal(1.0, 1.0, N) for _ in range(10)])
+    want = po.orc_decode(po.IMS, hd, Z, llr, 8)
+    with ldpc.Decoder(hd, Z, po.IMS, use_fast=2) as d:
+        assert d.kernel_info()["frames_per_cta"] >= 2
+        got = d.decode(llr, 8, want_post=True, want_aux=True)
+    for key in ("aux", "iters", "hard", "post"):
+        assert np.array_equal(got[key], want[key]), key
