@@ -175,7 +175,8 @@ int launch_decoder(ldpcb200_handle_s* h, FrameIO& io)
     } else if (use_fast && (h->decoder_id == LDPCB200_TASP_DEC || h->decoder_id == LDPCB200_ASP_DEC || h->decoder_id == LDPCB200_LCHE_DEC || h->decoder_id == LDPCB200_IASP_DEC ||
                             ((h->decoder_id == LDPCB200_BP_DEC || h->decoder_id == LDPCB200_SP_DEC) && !io.bp_syndrome))) {
         int fgrid = std::min(h->num_sms * h->fast.ctas_per_sm, io.nf);
-        CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream));
+        if (h->fast.bpsp4) CU(launch_bpsp4(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream));
+        else CU(launch_tasp_fast(h->fast, h->decoder_id, h->gd, io, std::max(fgrid, 1), h->stream));
     } else if (is_minsum(h->decoder_id)) {
         CU(h->ws.reserve(h->smem_ws ? 256 : h->ws_stride * h->grid));
         CU(launch_minsum_generic(h->decoder_id, h->p.precision, h->gd, h->dp, io, (char*)h->ws.p, h->ws_stride, h->smem_ws, grid, h->nt, h->stream));
@@ -327,8 +328,12 @@ int ldpcb200_create(const int16_t* hd, int b, int c, int Z, int decoder_id, cons
             else if (decoder_id == LDPCB200_IMS_DEC) h->fast = plan_ms_fast(h->g, 2, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
             else if (decoder_id == LDPCB200_MS_DEC && p.precision == 64) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);    // double: tasp_fast.cu
             else if (decoder_id == LDPCB200_MS_DEC) h->fast = plan_ms_fast(h->g, 1, p.precision, h->smem_per_sm, h->smem_per_block, p.use_fast >= 2, h->dp);
-            else if (decoder_id == LDPCB200_TASP_DEC || decoder_id == LDPCB200_ASP_DEC || decoder_id == LDPCB200_LCHE_DEC || decoder_id == LDPCB200_IASP_DEC ||
-                     decoder_id == LDPCB200_BP_DEC || decoder_id == LDPCB200_SP_DEC) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
+            else if (decoder_id == LDPCB200_BP_DEC || decoder_id == LDPCB200_SP_DEC) {
+                h->fast = plan_bpsp4(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);                     // four threads per check row
+                if (!h->fast.ok) h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
+            }
+            else if (decoder_id == LDPCB200_TASP_DEC || decoder_id == LDPCB200_ASP_DEC || decoder_id == LDPCB200_LCHE_DEC || decoder_id == LDPCB200_IASP_DEC)
+                h->fast = plan_tasp_fast(h->g, decoder_id, h->smem_per_sm, h->smem_per_block);
         }
         return 0;
     }();

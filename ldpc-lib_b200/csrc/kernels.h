@@ -32,6 +32,7 @@ struct FastPlan {
     int spec_index = -1;
     int tmem = 0;                       // 1: LMS_DEC with the c2v messages in tensor memory (lms_tmem.cuh)
     int msg32 = 0;                      // BP_DEC / SP_DEC (tasp_fast.cu): messages rounded to fp32, one tensor-memory column each
+    int bpsp4 = 0;                      // BP_DEC / SP_DEC: four threads per check row (bpsp4.cu)
     const void* jit_kernel = nullptr;
     std::string note;                   // why a faster variant was not used
     std::vector<unsigned char> tab;     // the kernel's parameter-space copy of the edge lists
@@ -45,6 +46,9 @@ cudaError_t launch_ms_fast(const FastPlan& p, const DecParams& dp, const FrameIO
 // TASP_DEC / ASP_DEC in double with the messages in tensor memory (tasp_fast.cu); table-driven, any code that fits
 FastPlan plan_tasp_fast(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block);
 cudaError_t launch_tasp_fast(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s, double alpha = 0.0);
+// BP_DEC / SP_DEC with four threads per check row (bpsp4.cu)
+FastPlan plan_bpsp4(const QcHost& g, int decoder_id, int smem_per_sm, int smem_per_block);
+cudaError_t launch_bpsp4(const FastPlan& p, int decoder_id, const QcDev& g, const FrameIO& io, int grid, cudaStream_t s);
 // TASP_DEC on n_codes matrices of the handle's shape in one launch: grid (grid_x, n_codes), d_gs / d_ios device arrays
 cudaError_t launch_tasp_multi(const FastPlan& p, const QcDev* d_gs, const FrameIO* d_ios, int n_codes, int grid_x, cudaStream_t s);
 

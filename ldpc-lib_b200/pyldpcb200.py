@@ -166,7 +166,9 @@ class Decoder:
         if d["fast"] == 1 and self.decoder_id == IASP_DEC:
             d["name"] = "iasp_fast_kernel (table-driven, 12-bit fixed point, messages in tensor memory)"
         if d["fast"] == 1 and self.decoder_id in (BP_DEC, SP_DEC):
-            d["name"] = "bpsp_fast_kernel<%s> (table-driven, double, messages in tensor memory)" % ("SP" if self.decoder_id == SP_DEC else "BP")
+            four = d["threads"] > (self.Z + 31) // 32 * 32
+            d["name"] = "%s<%s> (table-driven, double, messages in tensor memory%s)" % ("bpsp4_kernel" if four else "bpsp_fast_kernel", "SP" if self.decoder_id == SP_DEC else "BP",
+                                                                                         ", four threads per check row" if four else "")
         if d["fast"] == 1 and self.decoder_id == ASP_DEC:
             d["name"] = "asp_fast_kernel (table-driven, double, messages in tensor memory)"
         if "%s" in d["name"]:

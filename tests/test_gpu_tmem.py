@@ -63,20 +63,27 @@ def test_sumprod_fast_equals_parity_kernel(ldpc, po, monkeypatch, dec):
         assert np.array_equal(a["iters"][:60], want["iters"]) and np.array_equal(a["hard"][:60], want["hard"])
 
 
+@pytest.mark.parametrize("four", [True, False])
 @pytest.mark.parametrize("dec", ["BP", "SP"])
-def test_bp_sp_fast_kernels_against_the_parity_kernels(ldpc, po, monkeypatch, dec):
-    """bpsp_fast_kernel (tasp_fast.cu): BP_DEC regroups the reference's log-domain expressions into the product form (one exp,
+def test_bp_sp_fast_kernels_against_the_parity_kernels(ldpc, po, monkeypatch, dec, four):
+    """bpsp4_kernel (bpsp4.cu: four threads per check row, the default) and bpsp_fast_kernel (tasp_fast.cu: one thread per check
+    row, LDPCB200_NO_BPSP4=1): BP_DEC regroups the reference's log-domain expressions into the product form (one exp,
     one log per edge instead of two each), SP_DEC divides the edge's own message out of the column product -- the float class
     of the parity bar: identical decisions and iteration counts (here: on every frame), posteriors within 1e-4 relative
     (here: 1e-7), against the parity kernel (the reference's literal expressions) and the oracle; fixed-iteration mode
     reports the first success; a single frame; simulate == decode(generate_llr)."""
     did = getattr(po, dec)
+    if four:
+        monkeypatch.delenv("LDPCB200_NO_BPSP4", raising=False)
+    else:
+        monkeypatch.setenv("LDPCB200_NO_BPSP4", "1")
     for code, Z, snr in [("c4_wifi_12x24", 81, 2.0), ("ref32x16_b", 126, 2.5), ("c4_wifi_12x24", 81, 6.0)]:
         hd, llr = _llr(code, Z, snr, 300, 35)
         llr = llr.astype(np.float64)
         monkeypatch.delenv("LDPCB200_NO_TASP_FAST", raising=False)
         with ldpc.Decoder(hd, Z, did) as d:
             assert d.kernel_info()["tmem"], d.kernel_info()
+            assert (d.kernel_info()["threads"] > (Z + 31) // 32 * 32) == four, d.kernel_info()
             a = d.decode(llr, 20, want_post=True)
             fixed = d.decode(llr, 20, no_early_exit=True)
             one = d.decode(llr[7:8], 20)
