@@ -68,8 +68,11 @@ enum ldpcb200_flags {
     LDPCB200_OUT_ON_DEVICE   = 1 << 1,  /* hard / iters / posterior point to device memory       */
     LDPCB200_HARD_PACKED     = 1 << 2,  /* hard = ceil(N/32) uint32 words per frame, bit i of the
                                            frame at word i/32, bit i%32; default is one byte/bit  */
-    LDPCB200_NO_EARLY_EXIT   = 1 << 3,  /* run exactly maxiter iterations (worst-case timing);
-                                           iters then reports what the reference would return     */
+    LDPCB200_NO_EARLY_EXIT   = 1 << 3,  /* run exactly maxiter iterations, with the syndrome check in
+                                           every one (worst-case timing).  iters reports the count the
+                                           reference would return (its first zero syndrome); hard
+                                           decisions, posteriors and error counters are those AFTER
+                                           the extra iterations                                        */
     LDPCB200_BP_CHAIN_SYNDROME = 1 << 4 /* BP_DEC only: carry the previous frame's syndrome into the
                                            pre-iteration check, as decoders.cpp:1742-1759 does     */
 };
