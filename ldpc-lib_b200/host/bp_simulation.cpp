@@ -58,10 +58,12 @@ std::vector<int> devices_from_env()
 }
 
 unsigned long long g_next_frame = 0, g_epoch = ~0ull;
+volatile int g_interrupt = 0;                      // bp_simulation_request_interrupt()
 
 } // namespace
 
 bp_simulation_stats const& bp_simulation_last_stats() { return g_stats; }
+void bp_simulation_request_interrupt() { g_interrupt = 1; }
 
 std::pair<double, double> bp_simulation(
     int q_mod, matrix<int> const& H, matrix<int>& /*coef_matrix*/, int /*ncols2convert*/, int tailbite_length,
@@ -157,6 +159,7 @@ std::pair<double, double> bp_simulation(
     std::vector<float> ms(G);
     std::vector<std::string> errs(G);                           // ldpcb200_last_error() is per thread: taken inside the worker
     while (!stop && nde < n_frame_errors && experiment < limit) {
+        if (g_interrupt) { g_interrupt = 0; return std::make_pair(-1.0, -1.0); }            // :825-829
         const long long want = std::min<long long>(limit - experiment, per_gpu * G);
         // GPU g decodes frames [base + off[g], base + off[g] + cnt[g]) of the stream
         std::vector<long long> cnt(G), off(G);

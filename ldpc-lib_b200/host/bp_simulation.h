@@ -52,3 +52,9 @@ struct bp_simulation_stats {
     int gpus;
 };
 bp_simulation_stats const& bp_simulation_last_stats();
+
+// The reference lets the operator interrupt the current (code, SNR) point with the 'x' console key (console_exception_hook,
+// bp_simulation.cpp:590, :825-829) and then returns (-1, -1).  The drop-in has no console hook; a caller (or a signal handler: the
+// function only sets a flag) asks for the same through this call: the running -- or, if none is running, the next --
+// bp_simulation() returns (-1, -1) at its next round boundary and clears the request.
+void bp_simulation_request_interrupt();

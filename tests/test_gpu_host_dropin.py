@@ -68,10 +68,11 @@ def test_decision_argument_and_input_side_effects_match_the_reference(po, compat
         assert it == want["iter"]
         if dec in ("MS", "IMS", "IASP", "LMS", "TASP", "LCHE"):        # exact arithmetic, or 0 / 1
             assert np.array_equal(decword, want["decword"]), dec
-        else:                                                            # exp / log: libm vs CUDA
-            assert np.allclose(decword, want["decword"], rtol=1e-9, atol=1e-12), dec
+        else:                                                            # exp / log: libm vs CUDA; BP / SP: regrouped expressions (bpsp4.cu), whose
+            tol = 1e-5 if dec in ("BP", "SP") else 1e-9                  # cancellation in (AA - 1) / (AA + 1) amplifies last-bit differences; the bar is 1e-4
+            assert np.allclose(decword, want["decword"], rtol=tol, atol=1e-12), dec
         if dec in ("BP", "SP"):
-            assert np.allclose(after, want["soft_after"], rtol=1e-9, atol=1e-12)
+            assert np.allclose(after, want["soft_after"], rtol=1e-5, atol=1e-12)
         else:
             assert np.array_equal(after, want["soft_after"]), dec
 
@@ -161,6 +162,21 @@ def test_one_process_all_gpus_gives_the_single_gpu_result(tmp_path):
         assert r.returncode == 0, (devs, r.stderr)
         res[devs] = parse_result(out)[:2]
     assert res["all"] == res[""] and res["0,1"] == res[""]
+
+
+def test_interrupted_point_returns_minus_one_like_the_reference(tmp_path):
+    """bp_simulation_request_interrupt(): the reference's 'x' console hook ends the current point with (-1, -1)
+    (bp_simulation.cpp:590, :825-829); the call after it runs normally."""
+    exe = tmp_path / "interrupt_main"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(PKG, "host"), os.path.join(ROOT, "tests", "cpp", "interrupt_main.cpp"),
+                           os.path.join(PKG, "libldpcb200_host.a"), "-L", PKG, "-lldpcb200", "-lpthread", "-Wl,-rpath," + PKG, "-o", str(exe)])
+    hd, _ = load_code("c4_wifi_12x24")
+    hd.astype(np.int16).tofile(tmp_path / "hd.bin")
+    out = subprocess.run([str(exe), "12", "24", "81", str(tmp_path / "hd.bin")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    r = [float(x) for x in out.stdout.split()]
+    assert r[0] == -1.0 and r[1] == -1.0
+    assert 0.0 <= r[2] < 1.0 and 0.0 < r[3] <= 1.0
 
 
 def test_search_output_without_q_mod_is_accepted(tmp_path):
