@@ -1,6 +1,6 @@
-// IMS_DEC (imin_sum_decod_qc_lm, decoders.cpp:5430-5690, fixed point, bit-exact) with TWO frames per CTA packed into the
-// two fp16 halves of every 32-bit word: the low half of a register, a shared-memory word or a tensor-memory word belongs to
-// frame 2p, the high half to frame 2p + 1, and every arithmetic instruction (HADD2 / HFMA2 / HMNMX2, sign-bit LOP3) works
+// IMS_DEC (imin_sum_decod_qc_lm, decoders.cpp:5430-5690, fixed point, bit-exact) with TWO frames packed into the two fp16
+// halves of every 32-bit word: the low half of a register, a shared-memory word or a tensor-memory word belongs to one
+// frame, the high half to another, and every arithmetic instruction (HADD2 / HFMA2 / HMNMX2 / VHMNMX, sign-bit LOP3) works
 // on both frames at once.  Schedule, summation order and storage are those of ms_tmem.cuh (pass A: acc += message block row
 // by block row; pass B: soft = sat(iy + acc); pass C per check row: v2c, syndrome, new messages as minima over the OTHER
 // edges; messages in TENSOR MEMORY, accumulators / posteriors as doubled columns in the rotation of their last writer).
