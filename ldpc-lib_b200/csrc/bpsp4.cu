@@ -26,7 +26,7 @@ __device__ __forceinline__ void b4_put(unsigned* lw, int k, double m) { lw[2 * k
 
 // one block row, sweep C.  e0 .. e0 + rw: the row's edges; this thread owns edges e0 + p + 4 k, k < CMAX (those < e0 + rw)
 template <int CMAX, bool SP>
-__device__ __noinline__ void b4_rowC(const double* A, const unsigned char* zc, const unsigned* etab, int e0, int rw, int n, int p, int Z, unsigned tcol)
+__device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc, const unsigned* etab, int e0, int rw, int n, int p, int Z, unsigned tcol)
 {
     unsigned lw[2 * CMAX];
     tmem_ld_n<2 * CMAX>(tcol, lw);
@@ -90,7 +90,7 @@ __device__ __noinline__ void b4_rowC(const double* A, const unsigned char* zc, c
 
 // one block row, sweep A: posterior (+)= / (*)= the new messages, the first edge of a column starts from the channel value
 template <int CMAX, bool SP>
-__device__ __noinline__ void b4_rowA(double* A, unsigned char* zc, const double* y, const unsigned* etab, int e0, int rw, int n, int p, int Z, bool active, unsigned tcol)
+__device__ __forceinline__ void b4_rowA(double* A, unsigned char* zc, const double* y, const unsigned* etab, int e0, int rw, int n, int p, int Z, bool active, unsigned tcol)
 {
     unsigned lw[2 * CMAX];
     tmem_ld_n<2 * CMAX>(tcol, lw);
