@@ -71,16 +71,19 @@ __device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc
 #pragma unroll
     for (int k = 0; k < CMAX; k++) {
         double m;
+        // (1 + a) / (1 - a) with a = S / d[k] (:2111-2112, :1843-1846) as (d + S) / (d - S): one division fewer, and BP_DEC's
+        // logarithm of it without forming the quotient (fx_log_ratio).  |S| <= |d[k]| (every factor is at most 1 in magnitude
+        // and rounding is monotonic).  The reference's special values: d = 0 gives 0 / 0 = NaN, which its min / max turn into
+        // the UPPER clamp whatever the sign; d - S = 0 gives an infinity, the clamp again -- as does every quotient beyond
+        // e^19.07 = 1.9e8, so a denominator below 4e-9 of the numerator takes the clamp value without dividing.
+        const double nn = d[k] + S, qq = d[k] - S;
+        const bool sat = fabs(qq) <= fabs(nn) * 4e-9;
         if constexpr (SP) {
-            double a = d[k] == 0.0 ? S / d[k] : div_normal(S, d[k]);                     // :2111 (0 / 0 stays NaN -> 1.9e8 after the clamp)
-            const double den = 1 - a;
-            a = den == 0.0 ? (1 + a) / den : div_normal(1 + a, den);                     // :2112 (x / 0 stays an infinity)
+            const double a = sat ? 1.9e+8 : div_normal(nn, qq);
             m = b4_maxd(b4_mind(a, 1.9e+8), -5.2e-9);                                    // :2113
         } else {
-            const double a = d[k] == 0.0 ? S / d[k] : div_normal(S, d[k]);               // exp(s - x_e), :1843
-            const double den = 1 - a;
-            const double r = den == 0.0 ? (1 + a) / den : div_normal(1 + a, den);
-            m = (1 - 2 * (bs ^ bb[k])) * fx_log(r);                                      // :1846
+            const double lg = sat ? 19.07 : fx_log_ratio(nn, qq);
+            m = d[k] == 0.0 ? 19.07 : (bs ^ bb[k]) ? -lg : lg;                           // :1846
             m = b4_maxd(b4_mind(m, 19.07), -19.07);                                      // :1847
         }
         b4_put(lw, k, m);
@@ -161,11 +164,14 @@ __global__ void __launch_bounds__(MAXT, MINB) bpsp4_kernel(const Bpsp4Tab T, con
         int bad = 0;
         for (int j = 0; j < b; j++) {
             int synd = 0;
-            for (int e = rpw[j] + p; e < rpw[j + 1]; e += 4) {
-                const unsigned pk = etab[e];
+            const int e0 = rpw[j], rw = rpw[j + 1] - e0;
+#pragma unroll
+            for (int k = 0; k < CMAX; k++) {                                     // straight-line like the sweeps: no loop per row
+                const int q = p + 4 * k;
+                const unsigned pk = etab[e0 + (q < rw ? q : 0)];
                 int pos = n + (int)((pk >> 16) & 0x7fffu);
                 if (pos >= Z) pos -= Z;
-                synd ^= post((int)(pk & 0xffffu) + pos) < thr;
+                synd ^= (q < rw) & (post((int)(pk & 0xffffu) + pos) < thr);
             }
             bad |= synd << j;                                                    // (b <= 32 checked on the host)
         }

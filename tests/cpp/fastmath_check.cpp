@@ -23,8 +23,22 @@ int main()
         const double v = 1.0 - std::ldexp((double)(g() >> 11), -53 - (int)(g() % 40)), c = fx_log(v), d = std::log(v);
         if (std::fabs(c - d) > 2.3e-16 * std::fabs(d) + 1e-300) bad++;
     }
+    // fx_log_ratio(n, q) against log in long double of the exact quotient: the way bpsp4_kernel calls it (n = T + S, q = T - S)
+    double maxr = 0;
+    std::uniform_real_distribution<double> u01(0, 1), ux(-38, 0);
+    for (int i = 0; i < 4000000; i++) {
+        const double T = (i & 1) ? u01(g) : std::exp(ux(g)), S = T * ((i & 2) ? u01(g) : 1 - std::exp(ux(g)));
+        const double n = T + S, q = T - S;
+        if (!(q > 0) || q < n * 1e-9) continue;
+        const double c = fx_log_ratio(n, q);
+        const long double d = logl((long double)n / (long double)q);
+        const double err = (double)fabsl(c - d);
+        if (d > 1e-3L) maxr = std::fmax(maxr, err / (double)d);
+        else if (err > 4e-19 + 3e-16 * (double)d) bad++;
+    }
+    bad += !(fx_log_ratio(3.0, 3.0) == 0.0) + !(fx_log_ratio(1e-200, 1e-200) == 0.0);
     bad += !(fx_log(0.0) == -INFINITY) + !(fx_log(INFINITY) == INFINITY) + !std::isnan(fx_log(-1.0)) + !std::isnan(fx_log(NAN)) + !(fx_log(1.0) == 0.0);
     bad += !(fx_exp(-INFINITY) == 0.0) + !std::isnan(fx_exp(NAN)) + !(fx_exp(-800.0) == 0.0) + !(fx_exp(0.0) == 1.0);
-    printf("max relative error: exp %.3g, log %.3g; failures %d\n", maxe, maxl, bad);
-    return (maxe <= 2.3e-16 && maxl <= 2.3e-16 && bad == 0) ? 0 : 1;
+    printf("max relative error: exp %.3g, log %.3g, log of a ratio %.3g; failures %d\n", maxe, maxl, maxr, bad);
+    return (maxe <= 2.3e-16 && maxl <= 2.3e-16 && maxr <= 3.4e-16 && bad == 0) ? 0 : 1;
 }
