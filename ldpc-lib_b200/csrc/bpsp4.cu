@@ -26,7 +26,7 @@ __device__ __forceinline__ void b4_put(unsigned* lw, int k, double m) { lw[2 * k
 
 // one block row, sweep C.  e0 .. e0 + rw: the row's edges; this thread owns edges e0 + p + 4 k, k < CMAX (those < e0 + rw)
 template <int CMAX, bool SP>
-__device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc, const unsigned* etab, int e0, int rw, int n, int p, int Z, unsigned tcol)
+__device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc, const double* xt, const unsigned* etab, int e0, int rw, int n, int p, int Z, unsigned tcol)
 {
     unsigned lw[2 * CMAX];
     tmem_ld_n<2 * CMAX>(tcol, lw);
@@ -56,10 +56,9 @@ __device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc
             d[k] = div_normal(aa - 1, aa + 1);                                           // :2038
             bb[k] = 0;
         } else {
-            const double a = fx_exp(d[k] - b4_get(lw, k));                               // :1797
+            const double a = fx_exp_tab(d[k] - b4_get(lw, k), xt);                       // :1797 (|argument| < 700: plan_bpsp4)
             bb[k] = a < 1;                                                               // :1800
-            const double t = div_normal(a - 1, a + 1);                                   // :1798
-            d[k] = t < 0 ? -t : t;
+            d[k] = fabs(div_normal(a - 1, a + 1));                                       // :1798
         }
         if (have[k]) { S *= d[k]; bs ^= bb[k]; }                                         // :1810 / :2044
     }
@@ -78,13 +77,15 @@ __device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc
         // e^19.07 = 1.9e8, so a denominator below 4e-9 of the numerator takes the clamp value without dividing.
         const double nn = d[k] + S, qq = d[k] - S;
         const bool sat = fabs(qq) <= fabs(nn) * 4e-9;
+        // (no quotient is negative and none is a NaN any more, so one comparison does the reference's two-sided clamp)
         if constexpr (SP) {
-            const double a = sat ? 1.9e+8 : div_normal(nn, qq);
-            m = b4_maxd(b4_mind(a, 1.9e+8), -5.2e-9);                                    // :2113
+            const double a = div_normal(nn, qq);
+            m = (sat | !(a < 1.9e+8)) ? 1.9e+8 : a;                                      // :2113
         } else {
-            const double lg = sat ? 19.07 : fx_log_ratio(nn, qq);
-            m = d[k] == 0.0 ? 19.07 : (bs ^ bb[k]) ? -lg : lg;                           // :1846
-            m = b4_maxd(b4_mind(m, 19.07), -19.07);                                      // :1847
+            const double lg = fx_log_ratio(nn, qq);
+            m = (sat | !(lg < 19.07)) ? 19.07 : lg;                                      // :1847
+            const int neg = (bs ^ bb[k]) & (int)(d[k] != 0.0);                           // :1846
+            m = __hiloint2double(__double2hiint(m) ^ (neg << 31), __double2loint(m));
         }
         b4_put(lw, k, m);
     }
@@ -132,7 +133,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bpsp4_kernel(const Bpsp4Tab T, con
     const int Z = T.Z, N = T.N, E = T.E, b = T.b, nt = blockDim.x, tid = threadIdx.x;
     double* A = b4_smem;                 // posterior: BP_DEC LLR, SP_DEC product of the non-zero factors
     double* y = A + N;                   // channel values: clamped LLR (:1738) / its exponential (:1947-1951)
-    unsigned* etab = (unsigned*)(y + N);
+    double* xt = y + N;                  // 2^(j/32), j < 32 (fx_exp_tab)
+    unsigned* etab = (unsigned*)(xt + 32);
     int* rpw = (int*)(etab + E);
     unsigned* s_t = (unsigned*)(rpw + b + 1);
     unsigned char* zc = (unsigned char*)(s_t + 4);       // SP_DEC: exact zeros among a bit's factors
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bpsp4_kernel(const Bpsp4Tab T, con
         etab[e] = (unsigned)(c * Z) | ((unsigned)g.sh[e] << 16) | (g.cedge[g.cp[c]] == e ? 0x80000000u : 0u);
     }
     for (int j = tid; j <= b; j += nt) rpw[j] = g.rp[j];
+    if (tid < 32) xt[tid] = FX_T32_DEV[tid];
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"((unsigned)__cvta_generic_to_shared(s_t)), "r"((unsigned)T.tcols) : "memory");
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bpsp4_kernel(const Bpsp4Tab T, con
         bool locked = !parity;
         while (iter < io.maxiter && (parity || noexit)) {
             for (int j = 0; j < b; j++)                                                          // sweep C
-                b4_rowC<CMAX, SP>(A, zc, etab, rpw[j], rpw[j + 1] - rpw[j], n, p, Z, trow + (unsigned)(2 * CMAX * j));
+                b4_rowC<CMAX, SP>(A, zc, xt, etab, rpw[j], rpw[j + 1] - rpw[j], n, p, Z, trow + (unsigned)(2 * CMAX * j));
             tmem_wait_st();
             __syncthreads();
             for (int j = 0; j < b; j++) {                                                        // sweep A
@@ -236,13 +239,15 @@ FastPlan plan_bpsp4(const QcHost& g, int decoder_id, int smem_per_sm, int smem_p
     if (g.maxdeg > 20 || g.N > 65535 || g.b > 32) return p;
     for (int i = 0; i < g.c; i++)
         if (g.cp[i + 1] == g.cp[i]) return p;                           // sweep A starts a bit's posterior at its first edge
+    for (int i = 0; i < g.c; i++)
+        if (g.cp[i + 1] - g.cp[i] > 35) return p;                       // |posterior| <= 20 + 19.07 * weight must stay below fx_exp_tab's 700
     const int cmax = (g.maxdeg + 3) / 4;
     const int threads = ((4 * g.Z + 31) / 32) * 32;
     if (threads > 1024) return p;
     int tcols = 32;
     while (tcols < 2 * cmax * g.b * ((threads / 32 + 3) / 4)) tcols *= 2;
     if (tcols > 512) return p;
-    const size_t smem = sizeof(double) * (2 * (size_t)g.N + 16) + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16 + ((size_t)g.N + 15) / 16 * 16;
+    const size_t smem = sizeof(double) * (2 * (size_t)g.N + 48) + sizeof(unsigned) * (size_t)(g.E + g.b + 1 + 4) + 16 + ((size_t)g.N + 15) / 16 * 16;
     if (smem > (size_t)smem_per_block) return p;
     int m = 512 / tcols;
     m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));

@@ -9,12 +9,13 @@ using namespace ldpcb200;
 int main()
 {
     std::mt19937_64 g(1);
-    double maxe = 0, maxl = 0;
+    double maxe = 0, maxl = 0, maxt = 0;
     int bad = 0;
     std::uniform_real_distribution<double> ue(-250, 250), ul(-40, 40);
     for (int i = 0; i < 4000000; i++) {
         const double x = ue(g), a = fx_exp(x), b = std::exp(x);
         maxe = std::fmax(maxe, std::fabs(a - b) / b);
+        maxt = std::fmax(maxt, std::fabs(fx_exp_tab(x, FX_T32) - b) / b);
         const double v = std::exp(ul(g)), c = fx_log(v), d = std::log(v);
         if (std::fabs(d) > 1e-3) maxl = std::fmax(maxl, std::fabs(c - d) / std::fabs(d));
         else if (std::fabs(c - d) > 4e-19 + 3e-16 * std::fabs(d)) bad++;
@@ -39,6 +40,7 @@ int main()
     bad += !(fx_log_ratio(3.0, 3.0) == 0.0) + !(fx_log_ratio(1e-200, 1e-200) == 0.0);
     bad += !(fx_log(0.0) == -INFINITY) + !(fx_log(INFINITY) == INFINITY) + !std::isnan(fx_log(-1.0)) + !std::isnan(fx_log(NAN)) + !(fx_log(1.0) == 0.0);
     bad += !(fx_exp(-INFINITY) == 0.0) + !std::isnan(fx_exp(NAN)) + !(fx_exp(-800.0) == 0.0) + !(fx_exp(0.0) == 1.0);
-    printf("max relative error: exp %.3g, log %.3g, log of a ratio %.3g; failures %d\n", maxe, maxl, maxr, bad);
-    return (maxe <= 2.3e-16 && maxl <= 2.3e-16 && maxr <= 3.4e-16 && bad == 0) ? 0 : 1;
+    bad += !(fx_exp_tab(0.0, FX_T32) == 1.0);
+    printf("max relative error: exp %.3g, exp with table %.3g, log %.3g, log of a ratio %.3g; failures %d\n", maxe, maxt, maxl, maxr, bad);
+    return (maxe <= 2.3e-16 && maxt <= 3.4e-16 && maxl <= 2.3e-16 && maxr <= 3.4e-16 && bad == 0) ? 0 : 1;
 }
