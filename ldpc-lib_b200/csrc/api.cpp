@@ -210,6 +210,14 @@ void fill_channel(const ldpcb200_handle_s* h, const ldpcb200_sim_params* sp, Cha
     ch.first_frame = sp->first_frame;
     if (h->has_perm) { ch.perm_dir = (const int*)h->perm.p; ch.perm_inv = (const int*)h->perm.p + g.N; }
     if (h->has_cw) ch.cw = (const unsigned char*)h->cw.p;
+    if (ch.m >= 4) {                                                           // channel.cuh pam_demod_factored
+        const double N0 = 2.0 * sigma * sigma, sq1 = (double)((1 << (ch.m / 2)) - 1);
+        const char* ex = getenv("LDPCB200_QAM_EXACT");
+        ch.qam_w = 2.0 / N0;
+        ch.qam_n0inv = 1.0 / N0;
+        for (int j = 0; j < 8; j++) ch.qam_c[j] = exp(-(2.0 * j + 1) * (2.0 * j + 1) / N0);
+        ch.qam_fast = !(ex && *ex == '1') && sq1 * (sq1 + 6.0 * sigma) * ch.qam_w <= 600.0;
+    }
 }
 
 int check_sim(const ldpcb200_handle_s* h, const ldpcb200_sim_params* sp)

@@ -14,6 +14,7 @@
 // which makes results independent of batch size, launch geometry and GPU count.
 #pragma once
 #include "frame_io.h"
+#include "fastmath64.cuh"
 
 namespace ldpcb200 {
 
@@ -79,32 +80,6 @@ __device__ __forceinline__ float bpsk_llr(const ChannelParams& ch, float n)
     return __fmul_rn(__fmaf_rn(-ch.sigma, n, 1.0f), ch.llr_scale);
 }
 
-// n / d, correctly rounded (IEEE round-to-nearest, the reference's x86 divsd), WITHOUT the range-check branch and the
-// slow-path call that the compiler attaches to every double division: the instruction sequence of nvcc's own fast path
-// (MUFU.RCP64H seed, two Newton steps on the reciprocal, one residual correction of the quotient), which is exact
-// whenever both operands and the quotient are normal numbers far from the exponent limits (or n = 0).  Callers state
-// why that holds: TASP_DEC (tasp_fast.cu): d is a sum of products of probabilities clamped to [1e-4, 1 - 1e-4]
-// (1e-8 < d <= 1), 0 <= n <= 1 with n >= e^-160; ASP_DEC (dec_sumprod.cu): messages clamped to [1e-6, 1 - 1e-6], column
-// products of at most LDPCB200_MAX_ROW_WEIGHT such factors times a prior >= e^-40; Demodulate (pam_demod below): squared
-// distances over N0, likelihoods that are 0 or >= e^-T over their sum, ratios of such sums (0 / 0 gives NaN like the
-// reference's division).
-// Straight-line code lets the scheduler interleave the independent divisions of a block row / a sweep; with the branch
-// each division was its own basic block and the kernels sat in fixed-latency stalls.  tests/test_gpu_tmem.py checks
-// tasp_fast's posteriors bitwise against the parity kernel, which divides with operator /.
-__device__ __forceinline__ double div_normal(double n, double d)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = __fma_rn(-d, y, 1.0);
-    e = __fma_rn(e, e, e);
-    y = __fma_rn(y, e, y);
-    e = __fma_rn(-d, y, 1.0);
-    y = __fma_rn(y, e, y);
-    const double q = __dmul_rn(n, y);
-    const double r = __fma_rn(-d, q, n);
-    return __fma_rn(y, r, q);
-}
-
 // one output of Demodulate's if-ladder (e.g. QAM_demodulator.cpp:215-239)
 __device__ __forceinline__ double demod_out(double p0, double p1, double T, int out_type)
 {
@@ -159,6 +134,76 @@ __device__ __forceinline__ void pam_demod(double x, double N0, double T, int m, 
     }
 }
 
+// Demodulate for the IN-KERNEL channel, whose LLRs leave as fp32 (out[b] = (float)(-o[b]), LLR output type).  Same likelihoods,
+// same clip, same sums -- but the eight (four, sixteen) exponentials and the normalising divisions of pam_likelihoods become
+// ONE exponential and ONE division:
+//     exp(-(x - L)^2 / N0) = exp(-x^2 / N0) * W^L * exp(-L^2 / N0),     W = exp(2 x / N0),
+// the first factor cancels in every p1 / p0 (so does the reference's normalisation by the sum), the last is a per-SNR constant
+// (ChannelParams::qam_c), and W^L for the odd L are a multiplication chain from W and 1 / W.  The clip test t < T runs on
+// (x - L)^2 * (1 / N0).  log(p1 / p0) is fx_log_ratio.  The double results agree with pam_demod to a few 1e-15 relative
+// (rounding, not algorithm), i.e. the fp32 LLR differs in its last bit about once in 10^7 values; ldpcb200_generate_llr and
+// ldpcb200_demodulate, whose outputs are doubles, keep pam_demod.  The host enables it (qam_fast) when no power can leave
+// the double range: (sqrt(Q) - 1) * (sqrt(Q) - 1 + 6 sigma) * 2 / N0 <= 600, i.e. every operating point of an LDPC code;
+// LDPCB200_QAM_EXACT=1 turns it off.
+template <int SQ>
+__device__ __forceinline__ void pam_weights_factored(double x, const ChannelParams& ch, double (&P)[16])
+{
+    const double W = fx_exp(x * ch.qam_w);
+    const double V = div_normal(1.0, W);
+    const double W2 = W * W, V2 = V * V;
+    double Wp[SQ / 2], Vp[SQ / 2];                               // W^(2 j + 1), W^-(2 j + 1)
+    Wp[0] = W; Vp[0] = V;
+#pragma unroll
+    for (int j = 1; j < SQ / 2; j++) { Wp[j] = Wp[j - 1] * W2; Vp[j] = Vp[j - 1] * V2; }
+#pragma unroll
+    for (int i = 0; i < SQ; i++) {
+        const int L = 2 * i - (SQ - 1), j = ((L < 0 ? -L : L) - 1) / 2;
+        const double d = x - (double)L;
+        const double t = d * d * ch.qam_n0inv;
+        const double q = (L > 0 ? Wp[j] : Vp[j]) * ch.qam_c[j];
+        P[i] = t < ch.T ? q : 0.0;
+    }
+}
+
+__device__ __forceinline__ float demod_out_factored(double p0, double p1, double T)
+{
+    const double lg = fx_log_ratio(p1, p0);
+    return (float)(p0 == 0.0 ? -T : p1 == 0.0 ? T : -lg);
+}
+
+template <int SQ>
+__device__ __forceinline__ void pam_demod_factored_t(double x, const ChannelParams& ch, float* o)
+{
+    double P[16];
+    const double T = ch.T;
+    pam_weights_factored<SQ>(x, ch, P);
+    if constexpr (SQ == 4) {
+        o[0] = demod_out_factored(P[0] + P[1], P[2] + P[3], T);
+        o[1] = demod_out_factored(P[0] + P[3], P[1] + P[2], T);
+    } else if constexpr (SQ == 8) {
+        double p12 = P[0] + P[1], p34 = P[2] + P[3], p56 = P[4] + P[5], p78 = P[6] + P[7];
+        o[0] = demod_out_factored(p12 + p34, p56 + p78, T);
+        o[1] = demod_out_factored(p12 + p78, p34 + p56, T);
+        o[2] = demod_out_factored(P[0] + P[3] + P[4] + P[7], P[1] + P[2] + P[5] + P[6], T);
+    } else {
+        double p12 = P[0] + P[1], p34 = P[2] + P[3], p56 = P[4] + P[5], p78 = P[6] + P[7];
+        double p9A = P[8] + P[9], pBC = P[10] + P[11], pDE = P[12] + P[13], pFG = P[14] + P[15];
+        double p1234 = p12 + p34, p5678 = p56 + p78, p9ABC = p9A + pBC, pDEFG = pDE + pFG;
+        o[0] = demod_out_factored(p1234 + p5678, p9ABC + pDEFG, T);
+        o[1] = demod_out_factored(p1234 + pDEFG, p5678 + p9ABC, T);
+        o[2] = demod_out_factored(p12 + p78 + p9A + pFG, p34 + p56 + pBC + pDE, T);
+        o[3] = demod_out_factored(P[0] + P[3] + P[4] + P[7] + P[8] + P[11] + P[12] + P[15],
+                                  P[1] + P[2] + P[5] + P[6] + P[9] + P[10] + P[13] + P[14], T);
+    }
+}
+
+__device__ __forceinline__ void pam_demod_factored(double x, const ChannelParams& ch, float* o)
+{
+    if (ch.m == 4) pam_demod_factored_t<4>(x, ch, o);
+    else if (ch.m == 6) pam_demod_factored_t<8>(x, ch, o);
+    else pam_demod_factored_t<16>(x, ch, o);
+}
+
 // The decoder input that transmitted position j feeds (inverse permutation of bp_simulation.cpp:684, as a scatter)
 __device__ __forceinline__ int channel_dest(const ChannelParams& ch, int j)
 {
@@ -203,6 +248,11 @@ static __device__ __noinline__ float channel_llr_qam(const ChannelParams& ch, un
         pos = gray[z];
     }
     double x = (double)nz * ch.sigma_d + (double)(2 * pos - ((1 << half) - 1));
+    if (ch.qam_fast) {
+        float of[4];
+        pam_demod_factored(x, ch, of);
+        return of[bit];
+    }
     double o[4];
     pam_demod(x, 2.0 * ch.sigma_d * ch.sigma_d, ch.T, ch.m, 0, o);
     return (float)(-o[bit]);
@@ -217,9 +267,45 @@ static __device__ __noinline__ void channel_llr_qam_component(const ChannelParam
     const int half = ch.m >> 1;
     float nz = channel_noise(ch, frame, (unsigned int)cidx);
     double x = (double)nz * ch.sigma_d - (double)((1 << half) - 1);
+    if (ch.qam_fast) {
+        out[2] = out[3] = 0.0f;
+        pam_demod_factored(x, ch, out);
+        return;
+    }
     double o[4];
     pam_demod(x, 2.0 * ch.sigma_d * ch.sigma_d, ch.T, ch.m, 0, o);
     for (int b = 0; b < 4; b++) out[b] = b < half ? (float)(-o[b]) : 0.0f;
+}
+
+// The four PAM components 4*c4 .. 4*c4+3 of an all-zero frame: their noise samples are the four outputs of ONE Philox block
+// (channel_noise(idx) takes output idx & 3 of block idx >> 2), and the four factored demodulations are straight-line code next
+// to each other, so their exp -> 1/W -> powers -> sums -> log chains overlap (12 warps per SM at C3 cannot hide one chain's
+// latency).  out[4 q + b]: bit b of component 4*c4 + q, bit-identical to channel_llr_qam_component() of that component.
+template <int SQ>
+__device__ __forceinline__ void qam_components4_t(const ChannelParams& ch, const float z[4], float* out)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        out[4 * q + 2] = out[4 * q + 3] = 0.0f;
+        pam_demod_factored_t<SQ>((double)z[q] * ch.sigma_d - (double)(SQ - 1), ch, out + 4 * q);
+    }
+}
+static __device__ __noinline__ void channel_llr_qam_component4(const ChannelParams& ch, unsigned long long frame, int c4, float* out)
+{
+    float z[4];
+    channel_noise4(ch, frame, (unsigned int)c4, z);
+    if (ch.qam_fast) {
+        if (ch.m == 4) qam_components4_t<4>(ch, z, out);
+        else if (ch.m == 6) qam_components4_t<8>(ch, z, out);
+        else qam_components4_t<16>(ch, z, out);
+        return;
+    }
+    const int half = ch.m >> 1;
+    for (int q = 0; q < 4; q++) {
+        double o[4];
+        pam_demod((double)z[q] * ch.sigma_d - (double)((1 << half) - 1), 2.0 * ch.sigma_d * ch.sigma_d, ch.T, ch.m, 0, o);
+        for (int b = 0; b < 4; b++) out[4 * q + b] = b < half ? (float)(-o[b]) : 0.0f;
+    }
 }
 
 // Channel LLR (log P0/P1, the decoder-side sign) of decoder input i of frame f: the value received at transmitted

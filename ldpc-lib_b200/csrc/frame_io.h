@@ -26,6 +26,10 @@ struct ChannelParams {
     // Gray map is exercised): N bytes 0 / 1 in CODEWORD order on the device, or null for all-zero.  Only the per-bit path
     // (channel_llr) knows it: the fused first loads are for the all-zero codeword and the API routes around them.
     const unsigned char* cw;
+    // the factored Demodulate of the in-kernel channel (channel.cuh pam_demod_factored): 2 / N0, 1 / N0, exp(-L^2 / N0) for
+    // L = 1, 3, ..., 15; qam_fast = 0: the reference's evaluation order (pam_demod)
+    int qam_fast;
+    double qam_w, qam_n0inv, qam_c[8];
 };
 
 // Everything one decode launch reads and writes (all pointers are device pointers).

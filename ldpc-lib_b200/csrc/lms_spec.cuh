@@ -264,7 +264,20 @@ struct LmsSpec {
                 if (io.ch.m > 2) {
                     // QAM-16/64/256: one thread per PAM component, m/2 LLRs from one demodulation
                     const int half = io.ch.m >> 1, ncomp = 2 * (N / io.ch.m);
-                    for (int c = tid; c < ncomp; c += ZP) {
+                    for (int c4 = tid; c4 < ncomp / 4; c4 += ZP) {                    // four components from one Philox block
+                        float o4[16];
+                        channel_llr_qam_component4(io.ch, frame, c4, o4);
+                        for (int q = 0; q < 4; q++) {
+                            const int c = 4 * c4 + q, i0 = (c >> 1) * io.ch.m + (c & 1) * half;
+                            for (int b = 0; b < half; b++) {
+                                const int i = channel_dest(io.ch, i0 + b), col = i / Z, k = i - col * Z;
+                                const float x = i >= io.ch.punct_start ? io.ch.punct_value : o4[4 * q + b];
+                                soft2[col * CS + k] = x;
+                                if constexpr (DOUBLED) soft2[col * CS + Z + k] = x;
+                            }
+                        }
+                    }
+                    for (int c = (ncomp & ~3) + tid; c < ncomp; c += ZP) {
                         float o[4];
                         channel_llr_qam_component(io.ch, frame, c, o);
                         const int i0 = (c >> 1) * io.ch.m + (c & 1) * half;
