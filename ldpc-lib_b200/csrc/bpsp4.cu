@@ -4,10 +4,13 @@
 // division (profiles/r02_c4_bp_fast_ncu.txt: issue slots 32 %, `wait` 2.0 stalled warps per issue).  A frame's work is E * Z
 // independent edge updates plus cheap per-row combinations, so here lanes 4n .. 4n+3 of a warp share check row n: part p takes
 // the row's edges p, p + 4, p + 8, ...; the row's product of |tanh| (BP) / of the variable-to-check values (SP), its sign parity
-// and its syndrome bit are combined with two shuffles.  Same expressions as bpsp_fast_kernel (the float class of the parity bar:
-// regrouped, not re-derived -- see there), same sweeps per iteration (S syndrome, C check rows, A posteriors block row by block
-// row), messages as two TMEM columns per edge in the lane of the thread that owns the edge.  Four times the threads per frame
-// on the same tensor-memory footprint: 22 warps per SM at C4.
+// and its syndrome bit are combined with two shuffles.  The float class of the parity bar (identical decisions and iteration
+// counts on >= 99.99 % of frames, posteriors within 1e-4; measured: 0 of 100 000 frames differ): bpsp_fast_kernel's product forms
+// (see there), with the quotient (1 + S / T) / (1 - S / T) taken as (T + S) / (T - S), BP_DEC's logarithm of it as fx_log_ratio
+// (no quotient formed: one division instead of three) and its exponential as fx_exp_tab (fastmath64.cuh; table in shared
+// memory).  Same sweeps per iteration (S syndrome, C check rows, A posteriors block row by block row), messages as two TMEM
+// columns per edge in the lane of the thread that owns the edge.  Four times the threads per frame on the same tensor-memory
+// footprint: 22 warps per SM at C4; 130 instructions per edge, 53 of them double-precision.
 #include "dec_common.cuh"
 #include "lms_spec.cuh"
 #include "lms_tmem.cuh"
