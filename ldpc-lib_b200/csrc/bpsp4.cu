@@ -27,6 +27,11 @@ __device__ __forceinline__ double b4_maxd(double a, double b) { return a < b ? b
 __device__ __forceinline__ double b4_get(const unsigned* lw, int k) { return __hiloint2double((int)lw[2 * k + 1], (int)lw[2 * k]); }
 __device__ __forceinline__ void b4_put(unsigned* lw, int k, double m) { lw[2 * k] = (unsigned)__double2loint(m); lw[2 * k + 1] = (unsigned)__double2hiint(m); }
 
+// Slot k of a block row (edges 4 k .. 4 k + 3) is empty for all four parts when the row is lighter than the code's heaviest one
+// (REF-32x16-B: weights 6 .. 13, so CMAX = 4 and half of the slots of most rows): a branch that is uniform over the CTA skips it.
+// Slots 0 and 1 stay unconditional so that their chains share one basic block (a row of weight <= 4 is rare).
+#define B4_EMPTY(k, rw) ((k) >= 2 && 4 * (k) >= (rw))
+
 // one block row, sweep C.  e0 .. e0 + rw: the row's edges; this thread owns edges e0 + p + 4 k, k < CMAX (those < e0 + rw)
 template <int CMAX, bool SP>
 __device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc, const double* xt, const unsigned* etab, int e0, int rw, int n, int p, int Z, unsigned tcol)
@@ -40,6 +45,8 @@ __device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc
     for (int k = 0; k < CMAX; k++) {
         const int q = p + 4 * k;
         have[k] = q < rw;
+        d[k] = 1.0; nz[k] = 0;
+        if (B4_EMPTY(k, rw)) continue;
         const unsigned pk = etab[e0 + (have[k] ? q : 0)];
         int pos = n + (int)((pk >> 16) & 0x7fffu);
         if (pos >= Z) pos -= Z;
@@ -51,6 +58,8 @@ __device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc
     int bs = 0, bb[CMAX];
 #pragma unroll
     for (int k = 0; k < CMAX; k++) {
+        bb[k] = 0;
+        if (B4_EMPTY(k, rw)) continue;
         if constexpr (SP) {
             const double own = b4_get(lw, k);
             double aa;                                                                   // the channel value times the OTHER messages of the column (:2022-2036)
@@ -73,6 +82,7 @@ __device__ __forceinline__ void b4_rowC(const double* A, const unsigned char* zc
 #pragma unroll
     for (int k = 0; k < CMAX; k++) {
         double m;
+        if (B4_EMPTY(k, rw)) continue;
         // (1 + a) / (1 - a) with a = S / d[k] (:2111-2112, :1843-1846) as (d + S) / (d - S): one division fewer, and BP_DEC's
         // logarithm of it without forming the quotient (fx_log_ratio).  |S| <= |d[k]| (every factor is at most 1 in magnitude
         // and rounding is monotonic).  The reference's special values: d = 0 gives 0 / 0 = NaN, which its min / max turn into
@@ -108,6 +118,8 @@ __device__ __forceinline__ void b4_rowA(double* A, unsigned char* zc, const doub
     for (int k = 0; k < CMAX; k++) {
         const int q = p + 4 * k;
         have[k] = active && q < rw;
+        idx[k] = 0; cnt[k] = 0; acc[k] = 0.0; first[k] = false;
+        if (B4_EMPTY(k, rw)) continue;
         const unsigned pk = etab[e0 + (q < rw ? q : 0)];
         int pos = n + (int)((pk >> 16) & 0x7fffu);
         if (pos >= Z) pos -= Z;
@@ -174,6 +186,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bpsp4_kernel(const Bpsp4Tab T, con
 #pragma unroll
             for (int k = 0; k < CMAX; k++) {                                     // straight-line like the sweeps: no loop per row
                 const int q = p + 4 * k;
+                if (B4_EMPTY(k, rw)) continue;
                 const unsigned pk = etab[e0 + (q < rw ? q : 0)];
                 int pos = n + (int)((pk >> 16) & 0x7fffu);
                 if (pos >= Z) pos -= Z;
@@ -256,6 +269,8 @@ FastPlan plan_bpsp4(const QcHost& g, int decoder_id, int smem_per_sm, int smem_p
     m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));
     m = std::min(m, 2048 / threads);
     m = std::min(m, threads <= 512 ? 2 : 1);                           // register budget of the instance (b4_launch)
+    const char* one = getenv("LDPCB200_BPSP4_ONE_CTA");               // development: 385 .. 512 threads as one CTA with 128 registers
+    if (one && *one == '1' && threads > 384) m = 1;
     if (m < 1) m = 1;
     p.ok = 1; p.variant = 0; p.tmem = 1; p.msg32 = 0; p.bpsp4 = 1;
     p.threads = threads; p.frames_per_cta = 1; p.ctas_per_sm = m;
@@ -271,7 +286,8 @@ static cudaError_t b4_launch(const FastPlan& p, const Bpsp4Tab& T, const QcDev& 
 {
     // two CTAs per SM up to 512 threads: the launch bound caps the registers accordingly
     void (*k)(const Bpsp4Tab, const QcDev, const FrameIO) =
-        p.threads <= 256 ? bpsp4_kernel<256, 2, CMAX, SP> : p.threads <= 384 ? bpsp4_kernel<384, 2, CMAX, SP> : p.threads <= 512 ? bpsp4_kernel<512, 2, CMAX, SP>
+        p.threads <= 256 ? bpsp4_kernel<256, 2, CMAX, SP> : p.threads <= 384 ? bpsp4_kernel<384, 2, CMAX, SP>
+        : p.threads <= 512 ? (p.ctas_per_sm >= 2 ? bpsp4_kernel<512, 2, CMAX, SP> : bpsp4_kernel<512, 1, CMAX, SP>)
         : p.threads <= 768 ? bpsp4_kernel<768, 1, CMAX, SP> : bpsp4_kernel<1024, 1, CMAX, SP>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
     if (e != cudaSuccess) return e;
