@@ -159,7 +159,11 @@ int ldpcb200_decode_batch(ldpcb200_handle h, const void* llr, int llr_dtype, int
 /* The same decode on LLRs generated on the device from the handle's channel model.
  * per_frame (optional, host, n_frames uint32): bit 31 = frame in error, bit 30 = decoder reported
  * success, bits 0..23 = info-bit errors; lets the caller apply bp_simulation's stopping rules
- * (bp_simulation.cpp:591, 820) in exact frame order. */
+ * (bp_simulation.cpp:591, 820) in exact frame order.
+ * The in-kernel channel hands the decoder fp32 LLRs.  For QAM-16/64/256 it evaluates Demodulate's likelihood sums in a
+ * factored form (one exponential per PAM component; doubles within a few 1e-15 of QAM_demodulator.cpp:181-561, i.e. the same
+ * fp32 value but for a last bit about once in 1e7); ldpcb200_generate_llr / ldpcb200_demodulate keep the reference's
+ * evaluation order, and LDPCB200_QAM_EXACT=1 in the environment puts it into the kernels as well. */
 int ldpcb200_simulate(ldpcb200_handle h, const ldpcb200_sim_params* sp,
                       ldpcb200_counters* out, uint32_t* per_frame);
 
