@@ -269,8 +269,8 @@ FastPlan plan_bpsp4(const QcHost& g, int decoder_id, int smem_per_sm, int smem_p
     m = std::min(m, (int)((size_t)smem_per_sm / (smem + 2048)));
     m = std::min(m, 2048 / threads);
     m = std::min(m, threads <= 512 ? 2 : 1);                           // register budget of the instance (b4_launch)
-    const char* one = getenv("LDPCB200_BPSP4_ONE_CTA");               // development: 385 .. 512 threads as one CTA with 128 registers
-    if (one && *one == '1' && threads > 384) m = 1;
+    const char* one = getenv("LDPCB200_BPSP4_ONE_CTA");               // development: one CTA per SM (385 .. 512 threads: the instance with 128 registers)
+    if (one && *one == '1') m = 1;
     if (m < 1) m = 1;
     p.ok = 1; p.variant = 0; p.tmem = 1; p.msg32 = 0; p.bpsp4 = 1;
     p.threads = threads; p.frames_per_cta = 1; p.ctas_per_sm = m;
