@@ -186,6 +186,31 @@ struct LmsSpec {
         m1 = n1; m2 = n2; ps = S | MF;                                                       // :5179
     }
 
+    // Block rows that share no block column touch disjoint posteriors, so the barrier between them orders nothing: block row
+    // j + 1 may start while other warps still work on block row j (and on every earlier row since the last barrier), with
+    // the same result bit for bit.  need_barrier(j): does block row j + 1 share a column with any row of the barrier-free
+    // group that block row j closes?  (BG1-shaped C3: 11 of its 46 barriers go; the 16 x 32 and 12 x 24 matrices keep all.)
+    static __host__ __device__ constexpr bool rows_share(int a, int b)
+    {
+        for (int e = K::RP[a]; e < K::RP[a + 1]; e++)
+            for (int f = K::RP[b]; f < K::RP[b + 1]; f++)
+                if (K::COL[e] == K::COL[f]) return true;
+        return false;
+    }
+    static __host__ __device__ constexpr bool need_barrier(int j)
+    {
+        if (j + 1 >= B) return true;                             // the iteration ends: syndrome / next iteration
+        int start = 0;                                           // first row of the group that row j belongs to
+        for (int i = 0; i < j; i++) {
+            bool nb = false;
+            for (int r = start; r <= i; r++) nb = nb || rows_share(r, i + 1);
+            if (nb) start = i + 1;
+        }
+        for (int r = start; r <= j; r++)
+            if (rows_share(r, j + 1)) return true;
+        return false;
+    }
+
     template <int J>
     static __device__ __forceinline__ void layers(float* soft2, unsigned saddr, int n, bool active, float (&m1)[B], float (&m2)[B],
                                                   unsigned (&ps)[PS_SMEM ? 1 : B])
@@ -200,7 +225,8 @@ struct LmsSpec {
                 } else
                     layer<J>(soft2, saddr, n, m1[J], m2[J], ps[J]);
             }
-            __syncthreads();
+            constexpr bool BARRIER = need_barrier(J);
+            if constexpr (BARRIER) __syncthreads();
             layers<J + 1>(soft2, saddr, n, active, m1, m2, ps);
         }
     }
